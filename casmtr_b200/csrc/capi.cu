@@ -1,0 +1,294 @@
+// extern "C" entry points of libcasmtr_b200.so (see include/casmtr_b200.h): argument validation,
+// workspace carving and kernel sequencing.  No allocation, no synchronisation, caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+static thread_local char g_err[512] = "";
+
+void casmtr_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int casmtr_version(void) { return CASMTR_VERSION; }
+
+const char *casmtr_last_error_string(void) { return g_err; }
+
+int casmtr_device_info(int *sm_count, size_t *l2_bytes) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        casmtr_set_error("casmtr_device_info: no CUDA device");
+        return CASMTR_E_CUDA;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
+    return CASMTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ops
+int casmtr_score5d_fwd(const float *query, const float *key, const int64_t *index, float *out,
+                       int B, int N1, int N2, int H, int D, int K, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N1 >= 0 && N2 > 0 && H > 0 && D > 0 && K > 0, CASMTR_E_INVALID, "score5d: bad sizes");
+    CASMTR_REQUIRE((query && key && index && out) || (size_t)B * N1 == 0, CASMTR_E_INVALID, "score5d: null pointer");
+    return launch_score5d(query, key, index, out, B, N1, N2, H, D, K, (cudaStream_t)stream);
+}
+
+int casmtr_value_agg_fwd(const float *score, const float *value, const int64_t *index, float *out,
+                         int B, int N, int K, int H, int M, int D, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N >= 0 && K > 0 && H > 0 && M > 0 && D > 0, CASMTR_E_INVALID, "value_agg: bad sizes");
+    CASMTR_REQUIRE((score && value && index && out) || (size_t)B * N == 0, CASMTR_E_INVALID, "value_agg: null pointer");
+    return launch_value_agg(score, value, index, out, B, N, K, H, M, D, (cudaStream_t)stream);
+}
+
+int casmtr_score3d_fwd(const float *query, const float *key, const int64_t *index, float *out,
+                       int B, int N1, int N2, int C, int K, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N1 >= 0 && N2 > 0 && C > 0 && K > 0, CASMTR_E_INVALID, "score3d: bad sizes");
+    CASMTR_REQUIRE(C % 4 == 0, CASMTR_E_UNSUPPORTED, "score3d: C=%d must be a multiple of 4", C);
+    CASMTR_REQUIRE((query && key && index && out) || (size_t)B * N1 == 0, CASMTR_E_INVALID, "score3d: null pointer");
+    return launch_score3d(query, key, index, out, B, N1, N2, C, K, (cudaStream_t)stream);
+}
+
+int casmtr_nchw_to_tokens(const float *src, float *dst, int B, int C, int HW, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && C > 0 && HW > 0, CASMTR_E_INVALID, "nchw_to_tokens: bad sizes");
+    CASMTR_REQUIRE((src && dst) || B == 0, CASMTR_E_INVALID, "nchw_to_tokens: null pointer");
+    TransposeJobs jobs;
+    jobs.n = 1;
+    jobs.job[0] = TransposeJob{src, dst, C, HW, 0};
+    return launch_transpose_jobs(jobs, B, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ QTAtt
+static int check_qtatt_desc(const casmtr_qtatt_desc *d) {
+    CASMTR_REQUIRE(d != nullptr, CASMTR_E_INVALID, "qtatt: null descriptor");
+    CASMTR_REQUIRE(d->levels >= 1 && d->levels <= CASMTR_MAX_LEVELS, CASMTR_E_INVALID, "qtatt: levels=%d must be in [1,%d]", d->levels, CASMTR_MAX_LEVELS);
+    CASMTR_REQUIRE(d->D == 32, CASMTR_E_UNSUPPORTED, "qtatt: head dim %d unsupported, the fused kernels implement D == 32", d->D);
+    CASMTR_REQUIRE(d->B >= 1 && d->nhead >= 1, CASMTR_E_INVALID, "qtatt: B=%d nhead=%d", d->B, d->nhead);
+    CASMTR_REQUIRE(d->type == 0 || d->type == 1, CASMTR_E_INVALID, "qtatt: type=%d must be 0 (B) or 1 (A)", d->type);
+    for (int l = 0; l < d->levels; ++l) {
+        CASMTR_REQUIRE(d->qh[l] > 0 && d->qw[l] > 0 && d->kh[l] > 0 && d->kw[l] > 0, CASMTR_E_INVALID, "qtatt: empty grid at level %d", l);
+        if (l + 1 < d->levels)
+            CASMTR_REQUIRE(d->qh[l] == 2 * d->qh[l + 1] && d->qw[l] == 2 * d->qw[l + 1] && d->kh[l] == 2 * d->kh[l + 1] && d->kw[l] == 2 * d->kw[l + 1],
+                           CASMTR_E_INVALID, "qtatt: level %d grid must be exactly 2x level %d", l, l + 1);
+        CASMTR_REQUIRE(d->topks[l] >= 1 && d->topks[l] <= 32, CASMTR_E_UNSUPPORTED, "qtatt: topks[%d]=%d must be in [1,32]", l, d->topks[l]);
+    }
+    return CASMTR_OK;
+}
+
+struct QtattBuffers {
+    float *q[CASMTR_MAX_LEVELS], *k[CASMTR_MAX_LEVELS], *v[CASMTR_MAX_LEVELS];   // token-major, list order
+    float *acc[CASMTR_MAX_LEVELS];                                                 // processing order
+    int *tk_idx[CASMTR_MAX_LEVELS];
+    float *tk_sc[CASMTR_MAX_LEVELS];
+};
+
+static void carve_qtatt(const casmtr_qtatt_desc *d, Workspace &ws, QtattBuffers &bf) {
+    const size_t C = (size_t)d->nhead * d->D;
+    for (int l = 0; l < d->levels; ++l) {
+        bf.q[l] = ws.take<float>((size_t)d->B * d->qh[l] * d->qw[l] * C);
+        bf.k[l] = ws.take<float>((size_t)d->B * d->kh[l] * d->kw[l] * C);
+        bf.v[l] = ws.take<float>((size_t)d->B * d->kh[l] * d->kw[l] * C);
+    }
+    for (int i = 0; i < d->levels; ++i) {
+        const int l = d->levels - 1 - i;
+        const size_t Lq = (size_t)d->qh[l] * d->qw[l];
+        const bool last = i == d->levels - 1;
+        bf.acc[i] = last ? nullptr : ws.take<float>((size_t)d->B * Lq * C);
+        const bool need_topk = !last || i == 0;      // a single-level call still reports its top-k
+        bf.tk_idx[i] = need_topk ? ws.take<int>((size_t)d->B * Lq * d->nhead * d->topks[i]) : nullptr;
+        bf.tk_sc[i] = need_topk ? ws.take<float>((size_t)d->B * Lq * d->nhead * d->topks[i]) : nullptr;
+    }
+}
+
+size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc) {
+    if (check_qtatt_desc(desc) != CASMTR_OK) return 0;
+    Workspace ws(nullptr, 0);
+    QtattBuffers bf;
+    carve_qtatt(desc, ws, bf);
+    return ws.off;
+}
+
+int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
+                     const float *const *queries, const float *const *keys, const float *const *values,
+                     const float *level_weight, float *out,
+                     int64_t *const *topk_idx_out, float *const *topk_score_out,
+                     void *workspace, size_t workspace_bytes, casmtr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_qtatt_desc(d);
+    if (rc != CASMTR_OK) return rc;
+    CASMTR_REQUIRE(queries && keys && values && out && workspace, CASMTR_E_INVALID, "qtatt: null pointer");
+    CASMTR_REQUIRE(d->type == 1 || level_weight != nullptr, CASMTR_E_INVALID, "qtatt: QTAttB needs the level weight vector");
+    Workspace ws(workspace, workspace_bytes);
+    QtattBuffers bf;
+    carve_qtatt(d, ws, bf);
+    CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "qtatt: workspace %zu < %zu bytes", workspace_bytes, ws.off);
+    const int C = d->nhead * d->D;
+
+    TransposeJobs jobs;
+    jobs.n = 0;
+    for (int l = 0; l < d->levels; ++l) {
+        CASMTR_REQUIRE(queries[l] && keys[l] && values[l], CASMTR_E_INVALID, "qtatt: null level pointer %d", l);
+        jobs.job[jobs.n++] = TransposeJob{queries[l], bf.q[l], C, d->qh[l] * d->qw[l], 0};
+        jobs.job[jobs.n++] = TransposeJob{keys[l], bf.k[l], C, d->kh[l] * d->kw[l], 0};
+        jobs.job[jobs.n++] = TransposeJob{values[l], bf.v[l], C, d->kh[l] * d->kw[l], 0};
+    }
+    rc = launch_transpose_jobs(jobs, d->B, stream);
+    if (rc != CASMTR_OK) return rc;
+
+    const float *wts = d->type == 0 ? level_weight : nullptr;
+    for (int i = 0; i < d->levels; ++i) {
+        const int l = d->levels - 1 - i;
+        const bool last = i == d->levels - 1;
+        float *dst = last ? out : bf.acc[i];
+        if (i == 0) {
+            CoarseParams cp;
+            cp.q = bf.q[l]; cp.k = bf.k[l]; cp.v = bf.v[l];
+            cp.acc = dst; cp.topk_idx = bf.tk_idx[0]; cp.topk_score = bf.tk_sc[0];
+            cp.level_weight = wts; cp.levels = d->levels;
+            cp.B = d->B; cp.Sq = d->qh[l] * d->qw[l]; cp.Sk = d->kh[l] * d->kw[l];
+            cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type;
+            rc = launch_qtatt_coarse(cp, stream);
+        } else {
+            FineParams fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.q = bf.q[l]; fp.k = bf.k[l]; fp.v = bf.v[l];
+            fp.prev_idx = bf.tk_idx[i - 1]; fp.prev_score = bf.tk_sc[i - 1];
+            fp.acc_prev = bf.acc[i - 1]; fp.out = dst;
+            fp.topk_idx = last ? nullptr : bf.tk_idx[i];
+            fp.topk_score = last ? nullptr : bf.tk_sc[i];
+            fp.level_weight = wts; fp.levels = d->levels; fp.level = i;
+            fp.B = d->B; fp.nh = d->nhead;
+            fp.h0 = d->qh[l]; fp.w0 = d->qw[l]; fp.h1 = d->kh[l]; fp.w1 = d->kw[l]; fp.w_prev = d->kw[l + 1];
+            fp.kp = d->topks[i - 1]; fp.topk = d->topks[i]; fp.dil = 1;
+            fp.type_a = d->type; fp.final_level = last;
+            rc = launch_quad_attention(fp, stream);
+        }
+        if (rc != CASMTR_OK) return rc;
+        if (bf.tk_idx[i] && ((topk_idx_out && topk_idx_out[i]) || (topk_score_out && topk_score_out[i]))) {
+            rc = launch_topk_to_api(bf.tk_idx[i], bf.tk_sc[i], topk_idx_out ? topk_idx_out[i] : nullptr,
+                                    topk_score_out ? topk_score_out[i] : nullptr,
+                                    (size_t)d->B * d->qh[l] * d->qw[l], d->nhead, d->topks[i], stream);
+            if (rc != CASMTR_OK) return rc;
+        }
+    }
+    return CASMTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cascade attention
+size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1) {
+    if (B <= 0 || C <= 0 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0) return 0;
+    Workspace ws(nullptr, 0);
+    ws.take<float>((size_t)B * h0 * w0 * C);
+    ws.take<float>((size_t)B * h1 * w1 * C);
+    ws.take<float>((size_t)B * h1 * w1 * C);
+    return ws.off;
+}
+
+int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
+                             const int64_t *topk_pos, const float *rel_pos,
+                             float *message, int64_t *upsampled_idx,
+                             int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CASMTR_REQUIRE(D == 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: head dim %d unsupported (D == 32)", D);
+    CASMTR_REQUIRE(B >= 1 && nhead >= 1 && h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0, CASMTR_E_INVALID, "cascade_qtatt: bad sizes");
+    CASMTR_REQUIRE(h0 % 2 == 0 && w0 % 2 == 0, CASMTR_E_INVALID, "cascade_qtatt: query grid %dx%d must be even", h0, w0);
+    CASMTR_REQUIRE(k >= 1 && k <= 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: window size k=%d must be in [1,32]", k);
+    CASMTR_REQUIRE(dilated >= 1, CASMTR_E_INVALID, "cascade_qtatt: dilated=%d", dilated);
+    CASMTR_REQUIRE(query && key && value && topk_pos && message && workspace, CASMTR_E_INVALID, "cascade_qtatt: null pointer");
+    const int C = nhead * D;
+    Workspace ws(workspace, workspace_bytes);
+    float *qt = ws.take<float>((size_t)B * h0 * w0 * C);
+    float *kt = ws.take<float>((size_t)B * h1 * w1 * C);
+    float *vt = ws.take<float>((size_t)B * h1 * w1 * C);
+    CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "cascade_qtatt: workspace %zu < %zu bytes", workspace_bytes, ws.off);
+    TransposeJobs jobs;
+    jobs.n = 3;
+    jobs.job[0] = TransposeJob{query, qt, C, h0 * w0, 0};
+    jobs.job[1] = TransposeJob{key, kt, C, h1 * w1, 0};
+    jobs.job[2] = TransposeJob{value, vt, C, h1 * w1, 0};
+    int rc = launch_transpose_jobs(jobs, B, stream);
+    if (rc != CASMTR_OK) return rc;
+    FineParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.q = qt; fp.k = kt; fp.v = vt;
+    fp.topk_pos = topk_pos; fp.rel_pos = rel_pos;
+    fp.out = message; fp.upsampled_idx = upsampled_idx;
+    fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1;
+    fp.kp = k; fp.dil = dilated; fp.levels = 1;
+    return launch_quad_attention(fp, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ cascade matching
+int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
+                             const int64_t *idx01, const int64_t *idx10,
+                             const uint8_t *mask0, const uint8_t *mask1, float temperature,
+                             float *conf01, float *next_conf01, int64_t *next_idx01,
+                             float *conf10, float *next_conf10, int64_t *next_idx10,
+                             int B, int L0, int L1, int C, int K, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0 && K > 0, CASMTR_E_INVALID, "cascade_match: bad sizes");
+    CASMTR_REQUIRE(feat0 && feat1 && idx01 && idx10 && next_conf01 && next_idx01 && next_conf10 && next_idx10,
+                   CASMTR_E_INVALID, "cascade_match: null pointer");
+    CASMTR_REQUIRE((mask0 == nullptr) == (mask1 == nullptr), CASMTR_E_INVALID, "cascade_match: give both masks or neither");
+    CASMTR_REQUIRE(temperature > 0.f, CASMTR_E_INVALID, "cascade_match: temperature must be positive");
+    MatchParams p;
+    p.feat0 = feat0; p.feat1 = feat1; p.idx01 = idx01; p.idx10 = idx10; p.mask0 = mask0; p.mask1 = mask1;
+    p.inv_scale = 1.0f / ((float)C * temperature);
+    p.conf01 = conf01; p.conf10 = conf10; p.next_conf01 = next_conf01; p.next_conf10 = next_conf10;
+    p.next_idx01 = next_idx01; p.next_idx10 = next_idx10;
+    p.B = B; p.L0 = L0; p.L1 = L1; p.C = C; p.K = K;
+    return launch_cascade_match(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ extraction
+static int check_extract_desc(const casmtr_extract_desc *d) {
+    CASMTR_REQUIRE(d != nullptr, CASMTR_E_INVALID, "match_extract: null descriptor");
+    CASMTR_REQUIRE(d->B >= 1 && d->h0 > 0 && d->w0 > 0 && d->h1 > 0 && d->w1 > 0, CASMTR_E_INVALID, "match_extract: bad sizes");
+    CASMTR_REQUIRE(d->nms_window == 0 || (d->nms_window % 2 == 1 && d->nms_window <= 15), CASMTR_E_UNSUPPORTED,
+                   "match_extract: nms_window=%d must be 0 or odd <= 15", d->nms_window);
+    CASMTR_REQUIRE(d->n_pre >= 0 && d->n_pre <= 2, CASMTR_E_INVALID, "match_extract: n_pre=%d", d->n_pre);
+    for (int s = 0; s < d->n_pre; ++s)
+        CASMTR_REQUIRE(d->pre_conf[s] && d->pre_h[s] > 0 && d->pre_w[s] > 0, CASMTR_E_INVALID, "match_extract: bad previous-stage gate %d", s);
+    CASMTR_REQUIRE((d->pad_mask0 == nullptr) == (d->pad_mask1 == nullptr), CASMTR_E_INVALID, "match_extract: give both pad masks or neither");
+    CASMTR_REQUIRE((size_t)d->B * d->h0 * d->w0 < 0x7fffffffu, CASMTR_E_UNSUPPORTED, "match_extract: B*L0 too large");
+    return CASMTR_OK;
+}
+
+size_t casmtr_match_extract_workspace_bytes(const casmtr_extract_desc *desc) {
+    if (check_extract_desc(desc) != CASMTR_OK) return 0;
+    return match_extract_workspace(*desc);
+}
+
+int casmtr_match_extract(const casmtr_extract_desc *desc,
+                         const float *next_conf01, const int64_t *next_idx01, const int64_t *next_idx10,
+                         uint8_t *mask_out, int64_t *b_ids, int64_t *i_ids, int64_t *j_ids,
+                         float *mconf, float *mkpts0, float *mkpts1,
+                         int capacity, int32_t *count_out,
+                         void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    int rc = check_extract_desc(desc);
+    if (rc != CASMTR_OK) return rc;
+    CASMTR_REQUIRE(next_conf01 && next_idx01 && next_idx10 && b_ids && i_ids && j_ids && mconf && mkpts0 && mkpts1 && count_out && workspace,
+                   CASMTR_E_INVALID, "match_extract: null pointer");
+    CASMTR_REQUIRE(capacity >= desc->B, CASMTR_E_INVALID, "match_extract: capacity %d < B=%d", capacity, desc->B);
+    return launch_match_extract(*desc, next_conf01, next_idx01, next_idx10, mask_out, b_ids, i_ids, j_ids, mconf,
+                                mkpts0, mkpts1, capacity, count_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ fine matching
+int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
+                          const float *scale1_b, const int64_t *b_ids, float scale,
+                          float *expec_f, float *mkpts1_f, int M, int WW, int C, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(M >= 0 && WW > 0 && C > 0, CASMTR_E_INVALID, "fine_match: bad sizes");
+    CASMTR_REQUIRE(M == 0 || (feat_f0 && feat_f1 && mkpts1_c && expec_f && mkpts1_f), CASMTR_E_INVALID, "fine_match: null pointer");
+    CASMTR_REQUIRE(scale1_b == nullptr || b_ids != nullptr, CASMTR_E_INVALID, "fine_match: scale1_b needs b_ids");
+    return launch_fine_match(feat_f0, feat_f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, C, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Shared device/host helpers for libcasmtr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/casmtr_b200.h"
+
+#define FULL_MASK 0xffffffffu
+#define LOG2E_F 1.4426950408889634f
+
+void casmtr_set_error(const char *fmt, ...);
+
+#define CASMTR_REQUIRE(cond, code, ...)          \
+    do {                                         \
+        if (!(cond)) {                           \
+            casmtr_set_error(__VA_ARGS__);       \
+            return (code);                       \
+        }                                        \
+    } while (0)
+
+#define CASMTR_CHECK_LAUNCH(what)                                                   \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            casmtr_set_error("%s: %s", what, cudaGetErrorString(e__));              \
+            return CASMTR_E_CUDA;                                                   \
+        }                                                                           \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Workspace {
+    char *base;
+    size_t cap, off;
+    Workspace(void *p, size_t n) : base((char *)p), cap(n), off(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        T *p = (T *)(base ? base + off : nullptr);
+        off += bytes;
+        return p;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// streaming 128-bit load that does not allocate in L1 (data touched once)
+__device__ __forceinline__ float4 ldg4_stream(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// exp(x) for x <= 0 as used by every softmax here: one FMUL + EX2 (2 ulp).
+__device__ __forceinline__ float exp_neg(float x) { return exp2f(x * LOG2E_F); }

@@ -1,0 +1,87 @@
+// Internal launcher declarations shared between the .cu files and capi.cu.
+#pragma once
+#include "common.cuh"
+
+// ---- layout.cu
+struct TransposeJob {
+    const float *src;   // [B, C, HW]
+    float *dst;         // [B, HW, C]
+    int C, HW;
+    int tile_begin;     // filled by the launcher
+};
+struct TransposeJobs {
+    TransposeJob job[12];
+    int n;
+};
+int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream);
+int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
+                       size_t n_tok, int nh, int k, cudaStream_t stream);
+
+// ---- qtatt_coarse.cu
+struct CoarseParams {
+    const float *q, *k, *v;     // token-major [B,Sq,C] / [B,Sk,C]
+    float *acc;                 // [B,Sq,C]: level-0 contribution to the merged message
+    int *topk_idx;              // [B,Sq,nh,k] key index at this level
+    float *topk_score;          // [B,Sq,nh,k]
+    const float *level_weight;  // raw QTAttB.weight (device) or NULL
+    int levels;
+    int B, Sq, Sk, nh, topk;
+    int type_a;
+};
+size_t coarse_smem_bytes(int Sk);
+int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
+
+// ---- qtatt_fine.cu
+struct FineParams {
+    const float *q;             // token-major raster [B, h0*w0, C]
+    const float *k, *v;         // token-major raster [B, h1*w1, C]
+    const int *prev_idx;        // [B, Np, nh, kp]   (QTAtt levels)  key index on the (h1/2 x w1/2) grid
+    const float *prev_score;    // [B, Np, nh, kp]   (type A only)
+    const int64_t *topk_pos;    // [B, Np, kp, 2]    (cascade)  row, col on the previous grid
+    const float *rel_pos;       // [B, nh, h0*w0, 4kp] or NULL (cascade)
+    const float *acc_prev;      // [B, Np, C] merged message of the coarser levels, or NULL (cascade)
+    float *out;                 // [B, h0*w0, C] raster: acc_prev[parent] + w * message
+    int *topk_idx;              // [B, h0*w0, nh, k] or NULL (last level / cascade)
+    float *topk_score;          // same shape, or NULL
+    int64_t *upsampled_idx;     // [B, h0*w0, 4kp] or NULL (cascade)
+    const float *level_weight;  // raw weights or NULL
+    int levels, level;          // this level's position in the weight vector
+    int B, nh, h0, w0, h1, w1, w_prev;
+    int kp, topk;               // candidates = 4*kp; topk selected for the next level
+    int dil;                    // child offset dilation (cascade), 1 otherwise
+    int type_a, final_level;
+};
+int launch_quad_attention(const FineParams &p, cudaStream_t stream);
+
+// ---- ops.cu
+int launch_score5d(const float *q, const float *key, const int64_t *idx, float *out,
+                   int B, int N1, int N2, int H, int D, int K, cudaStream_t stream);
+int launch_value_agg(const float *score, const float *value, const int64_t *idx, float *out,
+                     int B, int N, int K, int H, int M, int D, cudaStream_t stream);
+int launch_score3d(const float *q, const float *key, const int64_t *idx, float *out,
+                   int B, int N1, int N2, int C, int K, cudaStream_t stream);
+
+// ---- cascade_match.cu
+struct MatchParams {
+    const float *feat0, *feat1;
+    const int64_t *idx01, *idx10;
+    const uint8_t *mask0, *mask1;
+    float inv_scale;            // 1 / (C * temperature)
+    float *conf01, *conf10;
+    float *next_conf01, *next_conf10;
+    int64_t *next_idx01, *next_idx10;
+    int B, L0, L1, C, K;
+};
+int launch_cascade_match(const MatchParams &p, cudaStream_t stream);
+
+// ---- extract.cu
+int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01, const int64_t *next_idx01,
+                         const int64_t *next_idx10, uint8_t *mask_out, int64_t *b_ids, int64_t *i_ids,
+                         int64_t *j_ids, float *mconf, float *mkpts0, float *mkpts1, int capacity,
+                         int32_t *count_out, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t match_extract_workspace(const casmtr_extract_desc &d);
+
+// ---- fine_match.cu
+int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, const float *scale1_b,
+                      const int64_t *b_ids, float scale, float *expec_f, float *mkpts1_f,
+                      int M, int WW, int C, cudaStream_t stream);

@@ -1,0 +1,76 @@
+// Layout kernels: NCHW -> token-major feature rows, internal top-k lists -> reference layout.
+//
+// The reference rearranges every pyramid level 'b c h w -> b (h w) c' and .contiguous()s it
+// (cuda_imp/QuadTreeAttention/QuadtreeAttention/modules/quadtree_attention.py:166-168,185-189);
+// here all (up to 12) maps of one attention call go through ONE batched tile-transpose launch.
+// Token-major makes one (token, head) row exactly one 128-byte line, which is what the gather
+// kernels want.  HBM-bound: 4 B read + 4 B written per element.
+#include "common.cuh"
+#include "kernels.cuh"
+
+__global__ void __launch_bounds__(256) transpose_jobs_kernel(TransposeJobs jobs) {
+    __shared__ float tile[32][33];
+    int t = blockIdx.x;
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < jobs.n && t >= jobs.job[j + 1].tile_begin) ++j;
+    const TransposeJob jb = jobs.job[j];
+    t -= jb.tile_begin;
+    const int tiles_c = (jb.C + 31) >> 5;
+    const int tc = t % tiles_c, tt = t / tiles_c;
+    const int b = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = jb.src + (size_t)b * jb.C * jb.HW;
+    float *dst = jb.dst + (size_t)b * jb.C * jb.HW;
+    const int tok_r = tt * 32 + tx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int c = tc * 32 + ty + 8 * r;
+        if (c < jb.C && tok_r < jb.HW) tile[ty + 8 * r][tx] = __ldg(src + (size_t)c * jb.HW + tok_r);
+    }
+    __syncthreads();
+    const int c_w = tc * 32 + tx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int tok = tt * 32 + ty + 8 * r;
+        if (tok < jb.HW && c_w < jb.C) dst[(size_t)tok * jb.C + c_w] = tile[tx][ty + 8 * r];
+    }
+}
+
+int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
+    int total = 0;
+    for (int i = 0; i < jobs.n; ++i) {
+        jobs.job[i].tile_begin = total;
+        total += ((jobs.job[i].C + 31) / 32) * ((jobs.job[i].HW + 31) / 32);
+    }
+    if (total == 0 || B == 0) return CASMTR_OK;
+    transpose_jobs_kernel<<<dim3(total, B), 256, 0, stream>>>(jobs);
+    CASMTR_CHECK_LAUNCH("transpose_jobs_kernel");
+    return CASMTR_OK;
+}
+
+// internal [B,L,nh,k] int32 / fp32  ->  reference [B,L,k,nh] int64 / fp32
+__global__ void topk_to_api_kernel(const int *__restrict__ idx, const float *__restrict__ score,
+                                   int64_t *__restrict__ idx_out, float *__restrict__ score_out,
+                                   size_t n_tok, int nh, int k) {
+    const size_t total = n_tok * nh * k;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(o % nh);
+        const int kk = (int)((o / nh) % k);
+        const size_t tok = o / ((size_t)nh * k);
+        const size_t in = (tok * nh + h) * k + kk;
+        if (idx_out) idx_out[o] = idx[in];
+        if (score_out) score_out[o] = score[in];
+    }
+}
+
+int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
+                       size_t n_tok, int nh, int k, cudaStream_t stream) {
+    const size_t total = n_tok * nh * k;
+    if (total == 0) return CASMTR_OK;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    topk_to_api_kernel<<<blocks, 256, 0, stream>>>(idx, score, idx_out, score_out, n_tok, nh, k);
+    CASMTR_CHECK_LAUNCH("topk_to_api_kernel");
+    return CASMTR_OK;
+}

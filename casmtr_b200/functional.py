@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI: argument checks, output/workspace allocation through
+torch's caching allocator, current-stream plumbing.  Everything here requires CUDA tensors --
+a CPU tensor raises, nothing falls back.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ExtractDesc, QtattDesc, check, lib
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(t, name, dtype=None):
+    # same conditions as the reference's CHECK_INPUT (is_cuda + is_contiguous), plus dtype
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name} must be contiguous')
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f'{name} must be {dtype}, got {t.dtype}')
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------- op-level
+def score5d(query, key, index):
+    """[B,N1,4,H,D] x [B,N2,H,D] gathered by index [B,N1,K,H] -> [B,N1,4,K,H]."""
+    _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(index, 'index', torch.int64)
+    B, N1, F, H, D = query.shape
+    if F != 4:
+        raise RuntimeError('query must be [B, N1, 4, H, D]')
+    N2, K = key.shape[1], index.shape[2]
+    out = torch.empty(B, N1, 4, K, H, dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        check(lib().casmtr_score5d_fwd(_ptr(query), _ptr(key), _ptr(index), _ptr(out), B, N1, N2, H, D, K, _stream(query)),
+              'casmtr_score5d_fwd')
+    return out
+
+
+def value_agg(score, value, index, output=None):
+    """score/index [B,N,K,H], value [B,M,H,D] -> output [B,N,H,D] (written in place if given)."""
+    _chk(score, 'score', torch.float32), _chk(value, 'value', torch.float32), _chk(index, 'index', torch.int64)
+    B, N, K, H = score.shape
+    M, D = value.shape[1], value.shape[3]
+    if output is None:
+        output = torch.empty(B, N, H, D, dtype=torch.float32, device=score.device)
+    _chk(output, 'output', torch.float32)
+    with torch.cuda.device(score.device):
+        check(lib().casmtr_value_agg_fwd(_ptr(score), _ptr(value), _ptr(index), _ptr(output), B, N, K, H, M, D, _stream(score)),
+              'casmtr_value_agg_fwd')
+    return output
+
+
+def score3d(query, key, index):
+    """[B,N1,C] x [B,N2,C] gathered by index [B,N1,K] -> [B,N1,K]."""
+    _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(index, 'index', torch.int64)
+    B, N1, Cc = query.shape
+    N2, K = key.shape[1], index.shape[2]
+    out = torch.empty(B, N1, K, dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        check(lib().casmtr_score3d_fwd(_ptr(query), _ptr(key), _ptr(index), _ptr(out), B, N1, N2, Cc, K, _stream(query)),
+              'casmtr_score3d_fwd')
+    return out
+
+
+def nchw_to_tokens(x):
+    _chk(x, 'x', torch.float32)
+    B, Cc = x.shape[:2]
+    HW = x[0, 0].numel()
+    out = torch.empty(B, HW, Cc, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().casmtr_nchw_to_tokens(_ptr(x), _ptr(out), B, Cc, HW, _stream(x)), 'casmtr_nchw_to_tokens')
+    return out
+
+
+# ------------------------------------------------------------------------------------- fused QuadTree attention
+def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B', return_topk=False):
+    """Fused QTAttA / QTAttB forward.  queries/keys/values: lists finest->coarsest of [B,C,H,W] fp32.
+    Returns message [B, L_finest, nhead, D] (and, with return_topk, per-level lists of top-k key
+    indices [B,L,k,nhead] int64 and scores, processing order, last level omitted)."""
+    n = len(queries)
+    if not (len(keys) == n and len(values) == n and 1 <= n <= _lib.MAX_LEVELS):
+        raise RuntimeError(f'need 1..{_lib.MAX_LEVELS} pyramid levels, got {n}')
+    if len(topks) < n:
+        raise RuntimeError(f'topks {topks} shorter than the pyramid ({n} levels)')
+    qs = [_chk(q, f'queries[{i}]', torch.float32) for i, q in enumerate(queries)]
+    ks = [_chk(k, f'keys[{i}]', torch.float32) for i, k in enumerate(keys)]
+    vs = [_chk(v, f'values[{i}]', torch.float32) for i, v in enumerate(values)]
+    dev = qs[0].device
+    B, Cc = qs[0].shape[:2]
+    d = QtattDesc()
+    d.B, d.nhead, d.D, d.levels, d.type = B, nhead, Cc // nhead, n, 1 if attn_type == 'A' else 0
+    for l in range(n):
+        if ks[l].shape != vs[l].shape or qs[l].shape[:2] != (B, Cc) or ks[l].shape[:2] != (B, Cc):
+            raise RuntimeError(f'inconsistent shapes at level {l}')
+        d.qh[l], d.qw[l] = qs[l].shape[2:]
+        d.kh[l], d.kw[l] = ks[l].shape[2:]
+        d.topks[l] = int(topks[l])
+    if d.type == 0:
+        if weight is None:
+            raise RuntimeError('QTAttB needs the level weight parameter')
+        weight = _chk(weight.detach().to(torch.float32).contiguous(), 'weight', torch.float32)
+        if weight.numel() < n:
+            raise RuntimeError('weight shorter than the pyramid')
+    L0 = d.qh[0] * d.qw[0]
+    out = torch.empty(B, L0, nhead, Cc // nhead, dtype=torch.float32, device=dev)
+    arr = C.c_void_p * n
+    qa, ka, va = arr(*[q.data_ptr() for q in qs]), arr(*[k.data_ptr() for k in ks]), arr(*[v.data_ptr() for v in vs])
+    tk_idx, tk_sc, ia, sa = [], [], None, None
+    if return_topk:
+        ia, sa = arr(), arr()
+        for i in range(n - 1 if n > 1 else 1):
+            l = n - 1 - i
+            shp = (B, d.qh[l] * d.qw[l], int(topks[i]), nhead)
+            tk_idx.append(torch.empty(shp, dtype=torch.int64, device=dev))
+            tk_sc.append(torch.empty(shp, dtype=torch.float32, device=dev))
+            ia[i], sa[i] = tk_idx[-1].data_ptr(), tk_sc[-1].data_ptr()
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_qtatt_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            check(-1, 'casmtr_qtatt_workspace_bytes')
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_qtatt_fwd(C.byref(d), qa, ka, va, _ptr(weight if d.type == 0 else None), _ptr(out),
+                                     ia, sa, _ptr(ws), ws.numel(), _stream(out)), 'casmtr_qtatt_fwd')
+    if return_topk:
+        return out, tk_idx, tk_sc
+    return out
+
+
+def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True):
+    """Fused CascadeQTAttB forward -> (message [B,h0*w0,C], upsampled_idx [B,h0*w0,4k] int64 or None)."""
+    _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(value, 'value', torch.float32)
+    _chk(topk_pos, 'topk_pos', torch.int64)
+    B, Cc, h0, w0 = query.shape
+    h1, w1 = key.shape[2:]
+    k = topk_pos.shape[2]
+    if topk_pos.shape != (B, (h0 // 2) * (w0 // 2), k, 2):
+        raise RuntimeError(f'topk_pos must be [B,(h0/2)*(w0/2),k,2], got {tuple(topk_pos.shape)}')
+    if rel_pos is not None:
+        rel_pos = _chk(rel_pos.to(torch.float32).contiguous(), 'rel_pos', torch.float32)
+        if rel_pos.numel() != B * nhead * h0 * w0 * 4 * k:
+            raise RuntimeError('rel_pos must hold B*nhead*h0*w0*4k values')
+    dev = query.device
+    msg = torch.empty(B, h0 * w0, Cc, dtype=torch.float32, device=dev)
+    up = torch.empty(B, h0 * w0, 4 * k, dtype=torch.int64, device=dev) if need_idx else None
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_cascade_qtatt_workspace_bytes(B, Cc, h0, w0, h1, w1)
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_cascade_qtatt_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), _ptr(rel_pos), _ptr(msg), _ptr(up),
+                                             B, nhead, Cc // nhead, h0, w0, h1, w1, k, 1 if dilated is None else int(dilated),
+                                             _ptr(ws), ws.numel(), _stream(msg)), 'casmtr_cascade_qtatt_fwd')
+    return msg, up
+
+
+# ------------------------------------------------------------------------------------- cascade matching
+def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, temperature=1.0, need_conf=True):
+    """Fused sparse correlation + softmax + argmax, both directions.  Returns dict with conf01/conf10
+    (None unless need_conf), next_conf01/10 [B,L] fp32, next_idx01/10 [B,L] int64."""
+    _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
+    _chk(idx01, 'idx01', torch.int64), _chk(idx10, 'idx10', torch.int64)
+    B, L0, Cc = feat0.shape
+    L1, K = feat1.shape[1], idx01.shape[2]
+    dev = feat0.device
+    m0 = m1 = None
+    if mask0 is not None and mask1 is not None:
+        m0 = _chk(mask0.reshape(B, L0).to(torch.uint8).contiguous(), 'mask0', torch.uint8)
+        m1 = _chk(mask1.reshape(B, L1).to(torch.uint8).contiguous(), 'mask1', torch.uint8)
+    o = {
+        'conf01': torch.empty(B, L0, K, dtype=torch.float32, device=dev) if need_conf else None,
+        'conf10': torch.empty(B, L1, K, dtype=torch.float32, device=dev) if need_conf else None,
+        'next_conf01': torch.empty(B, L0, dtype=torch.float32, device=dev),
+        'next_conf10': torch.empty(B, L1, dtype=torch.float32, device=dev),
+        'next_idx01': torch.empty(B, L0, dtype=torch.int64, device=dev),
+        'next_idx10': torch.empty(B, L1, dtype=torch.int64, device=dev),
+    }
+    with torch.cuda.device(dev):
+        check(lib().casmtr_cascade_match_fwd(_ptr(feat0), _ptr(feat1), _ptr(idx01), _ptr(idx10), _ptr(m0), _ptr(m1),
+                                             float(temperature), _ptr(o['conf01']), _ptr(o['next_conf01']), _ptr(o['next_idx01']),
+                                             _ptr(o['conf10']), _ptr(o['next_conf10']), _ptr(o['next_idx10']),
+                                             B, L0, L1, Cc, K, _stream(feat0)), 'casmtr_cascade_match_fwd')
+    return o
+
+
+def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_thr, border_rm, nms_window=None,
+                  pre_confs=(), pre_thrs=(), double_check=True, pad_mask0=None, pad_mask1=None,
+                  scale0=None, scale1=None):
+    """NMS / thresholds / border / mutual check / ordered compaction.  Same keyword surface as
+    oracle.cascade.extract_matches.  One host sync (the match count), like the reference's torch.where."""
+    _chk(next_conf01, 'next_conf01', torch.float32), _chk(next_idx01, 'next_idx01', torch.int64), _chk(next_idx10, 'next_idx10', torch.int64)
+    B, L0 = next_conf01.shape
+    dev = next_conf01.device
+    d = ExtractDesc()
+    d.B, (d.h0, d.w0), (d.h1, d.w1) = B, hw0, hw1
+    d.nms_window = 0 if nms_window is None else int(nms_window)
+    d.test_thr, d.border_rm, d.double_check = float(test_thr), int(border_rm), int(bool(double_check))
+    keep = []
+    d.n_pre = len(pre_confs)
+    if d.n_pre > 2 or len(pre_thrs) < d.n_pre:
+        raise RuntimeError('at most 2 previous-stage gates, each with a threshold')
+    for s, (pc, hp, wp) in enumerate(pre_confs):
+        pc = _chk(pc.detach().to(torch.float32).contiguous(), 'pre_conf', torch.float32)
+        keep.append(pc)
+        d.pre_conf[s], d.pre_h[s], d.pre_w[s], d.pre_thr[s] = pc.data_ptr(), hp, wp, float(pre_thrs[s])
+    if pad_mask0 is not None and pad_mask1 is not None:
+        pm0 = _chk(pad_mask0.to(torch.uint8).contiguous(), 'pad_mask0', torch.uint8)
+        pm1 = _chk(pad_mask1.to(torch.uint8).contiguous(), 'pad_mask1', torch.uint8)
+        keep += [pm0, pm1]
+        d.pad_mask0, d.pad_mask1 = pm0.data_ptr(), pm1.data_ptr()
+    d.scale = float(hw0_i[0] / hw0[0])
+    if scale0 is not None:
+        s0 = _chk(scale0.to(torch.float32).contiguous(), 'scale0', torch.float32)
+        keep.append(s0)
+        d.scale0 = s0.data_ptr()
+    if scale1 is not None:
+        s1 = _chk(scale1.to(torch.float32).contiguous(), 'scale1', torch.float32)
+        keep.append(s1)
+        d.scale1 = s1.data_ptr()
+    cap = B * L0
+    mask = torch.empty(B, L0, dtype=torch.uint8, device=dev)
+    ids = torch.empty(3, cap, dtype=torch.int64, device=dev)
+    mconf = torch.empty(cap, dtype=torch.float32, device=dev)
+    mk = torch.empty(2, cap, 2, dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_match_extract_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            check(-1, 'casmtr_match_extract_workspace_bytes')
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_match_extract(C.byref(d), _ptr(next_conf01), _ptr(next_idx01), _ptr(next_idx10), _ptr(mask),
+                                         _ptr(ids[0]), _ptr(ids[1]), _ptr(ids[2]), _ptr(mconf), _ptr(mk[0]), _ptr(mk[1]),
+                                         cap, _ptr(count), _ptr(ws), ws.numel(), _stream(mask)), 'casmtr_match_extract')
+    M = int(count.item())
+    return {'b_ids': ids[0, :M], 'i_ids': ids[1, :M], 'j_ids': ids[2, :M], 'mconf': mconf[:M],
+            'mkpts0_c': mk[0, :M], 'mkpts1_c': mk[1, :M], 'mask': mask.bool()}
+
+
+def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None):
+    """-> (expec_f [M,3], mkpts1_f [M,2])."""
+    _chk(feat_f0, 'feat_f0', torch.float32), _chk(feat_f1, 'feat_f1', torch.float32)
+    M, WW, Cc = feat_f0.shape
+    dev = feat_f0.device
+    mk = _chk(mkpts1_c.to(torch.float32).contiguous(), 'mkpts1_c', torch.float32)
+    expec = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    out = torch.empty(M, 2, dtype=torch.float32, device=dev)
+    s1 = bi = None
+    if scale1_b is not None:
+        s1 = _chk(scale1_b.to(torch.float32).contiguous(), 'scale1', torch.float32)
+        bi = _chk(b_ids.contiguous(), 'b_ids', torch.int64)
+    with torch.cuda.device(dev):
+        check(lib().casmtr_fine_match_fwd(_ptr(feat_f0), _ptr(feat_f1), _ptr(mk), _ptr(s1), _ptr(bi), float(scale),
+                                          _ptr(expec), _ptr(out), M, WW, Cc, _stream(expec)), 'casmtr_fine_match_fwd')
+    return expec, out

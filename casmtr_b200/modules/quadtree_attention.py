@@ -1,0 +1,102 @@
+"""Drop-in replacements for the reference's QuadTree attention modules
+(cuda_imp/QuadTreeAttention/QuadtreeAttention/modules/quadtree_attention.py): same class names,
+constructor signatures, forward signatures, return layouts and state-dict keys, so that
+``src/model/modules/quadtree_attention.py:6`` can import them instead.  Each forward is ONE call
+into libcasmtr_b200.so (fused per pyramid level) instead of ~40 torch ops + 2 extension kernels
+per level.  Inference only.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as tF
+
+from .. import functional as F
+
+
+def _f32c(x):
+    return x.to(torch.float32).contiguous()
+
+
+class QTAttA(nn.Module):
+    """reference :8-140."""
+
+    def __init__(self, nhead, dim, topks=[32, 32, 32, 32], scale=None, use_dropout=False, attention_dropout=0.1):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.topks = topks
+        self.nhead = nhead
+        self.dim = dim
+
+    def forward(self, queries, keys, values, q_mask=None, kv_mask=None):
+        """queries/keys/values: pyramids (finest first) of [N,C,H,W] -> message [N, H*W, nhead, dim].
+        Masks are accepted and ignored, as in the reference (:101)."""
+        return F.qtatt_forward([_f32c(q) for q in queries], [_f32c(k) for k in keys], [_f32c(v) for v in values],
+                               self.topks, self.nhead, attn_type='A')
+
+
+class QTAttB(nn.Module):
+    """reference :144-286.  Owns the learned per-level merge weight ``weight`` [scale] (:159)."""
+
+    def __init__(self, nhead, dim, scale, topks=[32, 32, 32, 32], use_dropout=False, attention_dropout=0.1, lepe=False):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.topks = topks
+        self.nhead = nhead
+        self.dim = dim
+        self.lepe = lepe
+        if lepe:  # locally enhanced position encoding (:152-158); stays a cuDNN depth-wise conv
+            self.get_vs = nn.ModuleList([
+                nn.Conv2d(dim * nhead, dim * nhead, kernel_size=3, stride=1, padding=1, groups=dim * nhead)
+                for _ in range(scale)])
+        self.register_parameter('weight', nn.Parameter(torch.randn(scale)))
+
+    def forward(self, queries, keys, values, q_mask=None, kv_mask=None, rel_pos=None):
+        if rel_pos is not None:
+            # dead in every shipped config (RELATIVE_PE False at 1/8; reference transformer.py:210-216 builds
+            # an unusable table) -- refuse loudly rather than silently ignore the bias.
+            raise NotImplementedError('QTAttB rel_pos is not implemented by casmtr_b200')
+        n = len(queries)
+        out = F.qtatt_forward([_f32c(q) for q in queries], [_f32c(k) for k in keys], [_f32c(v) for v in values],
+                              self.topks, self.nhead, weight=self.weight[:n], attn_type='B')
+        if self.lepe:    # (m_i + lepe_i) * w_i == m_i * w_i + lepe_i * w_i; the second term is added here (:266-282)
+            w = torch.softmax(self.weight[:n], dim=0)
+            B, C, H, W = values[0].shape
+            for i in range(n):
+                lp = self.get_vs[i](values[-(i + 1)])
+                if lp.shape[-2:] != (H, W):
+                    lp = tF.interpolate(lp, size=(H, W), mode='nearest')      # parent -> children broadcast
+                out = out + (lp * w[i]).flatten(2).transpose(1, 2).reshape(B, H * W, self.nhead, C // self.nhead)
+        return out
+
+
+class QTAttGuided(nn.Module):
+    """reference :289-389.  Only reachable with SELF_ATTN_TYPE='topk', which no shipped config selects
+    (SURVEY.md §8 a6); the class keeps the constructor and the ``weight`` state-dict key so reference
+    checkpoints load, the forward is not implemented on the B200 path."""
+
+    def __init__(self, nhead, dim, scale, topks=[32], use_dropout=False):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.topks = topks
+        self.nhead = nhead
+        self.dim = dim
+        self.register_parameter('weight', nn.Parameter(torch.randn(scale)))
+
+    def forward(self, queries, keys, values, q_mask=None, kv_mask=None, rel_pos=None, topk_pos=None):
+        raise NotImplementedError('QTAttGuided.forward is not implemented by casmtr_b200 (unused by every shipped config)')
+
+
+class CascadeQTAttB(nn.Module):
+    """reference :392-452.  Window (K = 4k) cross attention of the cascade stages."""
+
+    def __init__(self, nhead, dim, dilated, use_dropout=False):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.nhead = nhead
+        self.dim = dim
+        self.dilated = 1 if dilated is None else dilated
+
+    def forward(self, query, key, value, topk_pos, rel_pos):
+        """query [N,C,h0,w0], key/value [N,C,h1,w1], topk_pos [N,(h0/2*w0/2),k,2] (row,col), rel_pos None or
+        [N,nhead,h0*w0,4k] -> (message [N,h0*w0,C], upsampled_idx [N,h0*w0,4k] int64)"""
+        return F.cascade_qtatt_forward(_f32c(query), _f32c(key), _f32c(value), topk_pos.to(torch.int64).contiguous(),
+                                       rel_pos, self.nhead, self.dilated)

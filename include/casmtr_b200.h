@@ -1,0 +1,190 @@
+/*
+ * casmtr_b200.h -- C ABI of libcasmtr_b200.so: the B200 (sm_100a) replacement for the three
+ * CUDA extensions of ewrfcas/CasMTR and for the torch op sequences around them on the
+ * coarse-to-fine matching hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; all tensors are dense,
+ *     row-major, fp32 / int64 exactly as the reference's Python modules hand them over;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every
+ *     launch goes to that stream, nothing synchronises;
+ *   - return value 0 = success, <0 = error (see CASMTR_E_*); the message of the last error
+ *     on the calling thread is returned by casmtr_last_error_string();
+ *   - no allocation inside the library: fused entry points take a caller-owned workspace
+ *     whose size the matching *_workspace_bytes() function reports.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   R1 cuda_imp/QuadTreeAttention/QuadtreeAttention/src/score_computation.cpp:11-20,35-38
+ *      (pybind `score_computation_cuda.score_forward`)         -> casmtr_score5d_fwd
+ *   R2 cuda_imp/QuadTreeAttention/QuadtreeAttention/src/value_aggregation.cpp:9-31,62-65
+ *      (pybind `value_aggregation_cuda.value_aggregation_forward`) -> casmtr_value_agg_fwd
+ *   R3 cuda_imp/score_cuda/src/score_computation.cpp:11-17,29-32
+ *      (pybind `fast_score_computation.score_forward`)         -> casmtr_score3d_fwd
+ *   R4 cuda_imp/QuadTreeAttention/QuadtreeAttention/modules/quadtree_attention.py:8-140 (QTAttA.forward),
+ *      :144-286 (QTAttB.forward)                               -> casmtr_qtatt_fwd
+ *   R5 same file :392-452 (CascadeQTAttB.forward)               -> casmtr_cascade_qtatt_fwd
+ *   R6 src/model/functions/cascade_matching.py:87-149 (CascadeMatching.forward, inference)
+ *                                                               -> casmtr_cascade_match_fwd
+ *   R7 src/model/functions/cascade_matching.py:170-261,316-331 (get_coarse_match, inference) +
+ *      src/model/functions/post_processing.py:41-44,111-121 + cascade_functions.py:120-172
+ *                                                               -> casmtr_match_extract
+ *   R8 src/model/functions/fine_matching.py:77-137, 201-261     -> casmtr_fine_match_fwd
+ */
+#ifndef CASMTR_B200_H
+#define CASMTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CASMTR_VERSION 100          /* 0.1.0 */
+#define CASMTR_MAX_LEVELS 4
+
+#define CASMTR_OK 0
+#define CASMTR_E_INVALID (-1)       /* bad argument (null pointer, non-positive size, odd grid ...) */
+#define CASMTR_E_UNSUPPORTED (-2)   /* configuration outside what the kernels implement */
+#define CASMTR_E_CUDA (-3)          /* a CUDA runtime call or launch failed */
+#define CASMTR_E_WORKSPACE (-4)     /* workspace too small */
+
+typedef void *casmtr_stream_t;      /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define CASMTR_API __attribute__((visibility("default")))
+#else
+#define CASMTR_API
+#endif
+
+CASMTR_API int casmtr_version(void);
+CASMTR_API const char *casmtr_last_error_string(void);
+/* SM count / L2 bytes of the current device (host-side helper for the bench harness). */
+CASMTR_API int casmtr_device_info(int *sm_count, size_t *l2_bytes);
+
+/* ---------------------------------------------------------------- op-level drop-ins (R1-R3) */
+
+/* out[b,n,f,k,h] = sum_d query[b,n,f,h,d] * key[b, index[b,n,k,h], h, d]
+ * query [B,N1,4,H,D], key [B,N2,H,D], index [B,N1,K,H] int64, out [B,N1,4,K,H] (fully written).
+ * Lifts the reference's limits H<=8 and N1<=65535; index values are clamped to [0,N2-1]. */
+CASMTR_API int casmtr_score5d_fwd(const float *query, const float *key, const int64_t *index, float *out,
+                       int B, int N1, int N2, int H, int D, int K, casmtr_stream_t stream);
+
+/* out[b,n,h,d] = sum_k score[b,n,k,h] * value[b, index[b,n,k,h], h, d]
+ * score/index [B,N,K,H], value [B,M,H,D], out [B,N,H,D] (overwritten, need not be zeroed). */
+CASMTR_API int casmtr_value_agg_fwd(const float *score, const float *value, const int64_t *index, float *out,
+                         int B, int N, int K, int H, int M, int D, casmtr_stream_t stream);
+
+/* out[b,n,k] = sum_c query[b,n,c] * key[b, index[b,n,k], c]
+ * query [B,N1,C], key [B,N2,C], index [B,N1,K] int64, out [B,N1,K].  C % 4 == 0. */
+CASMTR_API int casmtr_score3d_fwd(const float *query, const float *key, const int64_t *index, float *out,
+                       int B, int N1, int N2, int C, int K, casmtr_stream_t stream);
+
+/* NCHW -> token-major: src [B,C,HW] -> dst [B,HW,C] (exported for tests / callers that want
+ * to keep features token-major between layers). */
+CASMTR_API int casmtr_nchw_to_tokens(const float *src, float *dst, int B, int C, int HW, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- fused QuadTree attention (R4) */
+
+typedef struct {
+    int B;                          /* batch */
+    int nhead;                      /* heads; channels C = nhead * D */
+    int D;                          /* head dim; the fused kernels implement D == 32 */
+    int levels;                     /* pyramid depth, 1..CASMTR_MAX_LEVELS */
+    int type;                       /* 0 = QTAttB, 1 = QTAttA */
+    int qh[CASMTR_MAX_LEVELS];      /* query grid per level, [0] = FINEST (the reference's list order) */
+    int qw[CASMTR_MAX_LEVELS];
+    int kh[CASMTR_MAX_LEVELS];      /* key/value grid per level */
+    int kw[CASMTR_MAX_LEVELS];
+    int topks[CASMTR_MAX_LEVELS];   /* the reference's `topks`: [0] = coarsest level */
+} casmtr_qtatt_desc;
+
+CASMTR_API size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc);
+
+/* queries/keys/values: HOST arrays of `levels` device pointers, [l] = [B,C,h_l,w_l] NCHW fp32,
+ * l = 0 finest (exactly the lists QTAttB.forward receives).
+ * level_weight: device [levels], the raw `weight` parameter of QTAttB (softmax over levels is
+ *   applied inside, reference :264); ignored (may be NULL) for type A.
+ * out: [B, qh[0]*qw[0], nhead, D].
+ * topk_idx_out / topk_score_out: optional HOST arrays (or NULL) of `levels` device pointers in
+ *   the reference's processing order ([0] = coarsest); entry i, if non-NULL, receives the
+ *   level's top-k key indices [B, L_i, topks[i], nhead] int64 (raster order, as the reference
+ *   holds them after :226-227) resp. their scores (fp32).  The last level's entry is ignored
+ *   (the reference computes and discards it). */
+CASMTR_API int casmtr_qtatt_fwd(const casmtr_qtatt_desc *desc,
+                     const float *const *queries, const float *const *keys, const float *const *values,
+                     const float *level_weight, float *out,
+                     int64_t *const *topk_idx_out, float *const *topk_score_out,
+                     void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- fused cascade window attention (R5) */
+
+CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1);
+
+/* query [B,C,h0,w0], key/value [B,C,h1,w1] NCHW; topk_pos [B,(h0/2)*(w0/2),k,2] int64 (row,col at
+ * the previous level); rel_pos NULL or [B,nhead,h0*w0,4k]; message [B,h0*w0,C];
+ * upsampled_idx NULL or [B,h0*w0,4k] int64.  k <= 32, D == 32. */
+CASMTR_API int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
+                             const int64_t *topk_pos, const float *rel_pos,
+                             float *message, int64_t *upsampled_idx,
+                             int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- fused cascade matching (R6) */
+
+/* feat0 [B,L0,C], feat1 [B,L1,C] (un-normalised; the 1/sqrt(C) of reference :88 is applied inside);
+ * idx01 [B,L0,K], idx10 [B,L1,K] int64; mask0 [B,L0] / mask1 [B,L1] uint8 (both or neither NULL);
+ * conf01 / conf10: NULL or [B,L,K] softmax over the K candidates; next_conf* [B,L] fp32 (row max);
+ * next_idx* [B,L] int64 = idx[b,i,argmax].  K <= 128, C % 4 == 0. */
+CASMTR_API int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
+                             const int64_t *idx01, const int64_t *idx10,
+                             const uint8_t *mask0, const uint8_t *mask1, float temperature,
+                             float *conf01, float *next_conf01, int64_t *next_idx01,
+                             float *conf10, float *next_conf10, int64_t *next_idx10,
+                             int B, int L0, int L1, int C, int K, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- NMS + match extraction (R7) */
+
+typedef struct {
+    int B, h0, w0, h1, w1;          /* source / target grids of this stage */
+    int nms_window;                 /* 0 = plain threshold (post_processing.py:43-44); odd k = maxpool NMS */
+    float test_thr;
+    int border_rm;
+    int double_check;
+    int n_pre;                      /* previous-stage confidence gates, 0..2 (cascade_matching.py:199-206) */
+    const float *pre_conf[2];       /* device [B, pre_h*pre_w] */
+    int pre_h[2], pre_w[2];
+    float pre_thr[2];
+    const uint8_t *pad_mask0;       /* NULL, or device [B,h0,w0]: padded border variant (cascade_functions.py:142-172) */
+    const uint8_t *pad_mask1;       /* NULL, or device [B,h1,w1] */
+    float scale;                    /* hw0_i[0] / h0 (cascade_matching.py:317) */
+    const float *scale0;            /* NULL or device [B,2] */
+    const float *scale1;            /* NULL or device [B,2] */
+} casmtr_extract_desc;
+
+CASMTR_API size_t casmtr_match_extract_workspace_bytes(const casmtr_extract_desc *desc);
+
+/* next_conf01 [B,L0] fp32, next_idx01 [B,L0] int64, next_idx10 [B,L1] int64.
+ * Outputs (capacity entries each; capacity >= B, B*L0 always suffices): b_ids,i_ids,j_ids int64,
+ * mconf fp32, mkpts0/mkpts1 [capacity,2] fp32 in torch.where order; mask_out NULL or [B,L0] uint8 (the
+ * keep flags before the reference's "if mask.sum() == 0: mask[:, 0] = True" fallback, which only affects the list);
+ * count_out: device int32, number of matches (entries beyond capacity are dropped, count is not clamped). */
+CASMTR_API int casmtr_match_extract(const casmtr_extract_desc *desc,
+                         const float *next_conf01, const int64_t *next_idx01, const int64_t *next_idx10,
+                         uint8_t *mask_out, int64_t *b_ids, int64_t *i_ids, int64_t *j_ids,
+                         float *mconf, float *mkpts0, float *mkpts1,
+                         int capacity, int32_t *count_out,
+                         void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- fine matching (R8) */
+
+/* feat_f0/feat_f1 [M,WW,C]; mkpts1_c [M,2]; scale = hw0_i[0]/hw0_f[0]; scale1_b NULL or [B,2] with
+ * b_ids [M] int64; expec_f [M,3] = (x, y, std); mkpts1_f [M,2].  WW <= 32 (W in {3,5}), C % 4 == 0. */
+CASMTR_API int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
+                          const float *scale1_b, const int64_t *b_ids, float scale,
+                          float *expec_f, float *mkpts1_f, int M, int WW, int C, casmtr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASMTR_B200_H */
