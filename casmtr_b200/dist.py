@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: image pairs are independent, so the hot path shards the batch contiguously
+over ranks with no data-path collective; the only exchange is the final variable-length match
+list.  The reference's analogue is a pickled gloo ``gather`` of result dicts
+(src/utils/comm.py:180-220, src/lightning/lightning_cascade.py:388-396); here it is one all-gather
+of the counts and one padded all-gather of a packed 44-byte-per-match record, on whatever backend
+the process group uses (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+RECORD_BYTES = 3 * 8 + 5 * 4      # b_id, i_id, j_id (int64) + mconf, mkpts0[2], mkpts1[2] (fp32)
+
+
+def shard_range(n_pairs, rank, world):
+    """Contiguous split of n_pairs over `world` ranks: rank r gets [lo, hi)."""
+    base, rem = divmod(n_pairs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_matches(m, pair_offset=0):
+    """dict(b_ids,i_ids,j_ids,mconf,mkpts0,mkpts1) -> uint8 [M, 44]; b_ids become global pair ids."""
+    ids = torch.stack([m['b_ids'] + pair_offset, m['i_ids'], m['j_ids']], dim=1).contiguous()
+    fl = torch.cat([m['mconf'].reshape(-1, 1), m['mkpts0'].reshape(-1, 2), m['mkpts1'].reshape(-1, 2)], dim=1)
+    fl = fl.to(torch.float32).contiguous()
+    M = ids.shape[0]
+    return torch.cat([ids.view(torch.uint8).reshape(M, 24), fl.view(torch.uint8).reshape(M, 20)], dim=1)
+
+
+def unpack_matches(buf):
+    M = buf.shape[0]
+    ids = buf[:, :24].contiguous().view(torch.int64).reshape(M, 3)
+    fl = buf[:, 24:].contiguous().view(torch.float32).reshape(M, 5)
+    return {'b_ids': ids[:, 0], 'i_ids': ids[:, 1], 'j_ids': ids[:, 2], 'mconf': fl[:, 0],
+            'mkpts0': fl[:, 1:3], 'mkpts1': fl[:, 3:5]}
+
+
+def gather_matches(m, pair_offset=0, group=None):
+    """All ranks receive the concatenation (in rank order, i.e. global pair order) of every rank's
+    match list.  Without an initialised process group this is the identity."""
+    buf = pack_matches(m, pair_offset)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return unpack_matches(buf)
+    world = dist.get_world_size(group)
+    count = torch.tensor([buf.shape[0]], dtype=torch.int64, device=buf.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros(cap, RECORD_BYTES, dtype=torch.uint8, device=buf.device)
+    padded[:buf.shape[0]] = buf
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return unpack_matches(torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0))

@@ -1,0 +1,176 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference Python modules
+(imported from /root/reference through oracle/refload.py) on seeded synthetic inputs.
+
+    python tests/golden/make_golden.py          # only works where /root/reference exists
+
+The reference ships no golden vectors of its own, so these files -- outputs of the
+reference itself -- are what pins the oracle (tests/test_oracle_golden.py, CPU) and the CUDA path
+(tests/test_gpu_golden.py).  Inputs are stored next to the outputs so nothing depends on RNG
+reproducibility across torch versions.  int64 tensors are stored as int32 to keep the files small.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from casmtr_b200 import synth  # noqa: E402
+from oracle import refload  # noqa: E402
+
+
+def _np(t):
+    t = t.detach().cpu()
+    if t.dtype == torch.int64:
+        return t.to(torch.int32).numpy()
+    if t.dtype == torch.bool:
+        return t.to(torch.uint8).numpy()
+    return t.numpy()
+
+
+def save(name, **tensors):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **{k: _np(v) for k, v in tensors.items() if v is not None})
+    print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB')
+
+
+class Tap:
+    """Records what the reference's process_*_level methods return, without touching its code."""
+
+    def __init__(self, mod):
+        self.idx, self.score = [], []
+        for meth in ('process_coarse_level', 'process_fine_level'):
+            orig = getattr(mod, meth)
+
+            def wrapped(*a, _o=orig, **k):
+                r = _o(*a, **k)
+                self.score.append(r[2])
+                self.idx.append(r[3])
+                return r
+            setattr(mod, meth, wrapped)
+
+
+def gen_qtatt(ref):
+    nh, C, h, w, topks = 2, 64, 16, 24, [8, 4, 4]
+    qs, ks, vs, wt = synth.qtatt_inputs(1, C, h, w, 3, seed=101)
+    mb = ref.QTAttB(nh, C // nh, scale=3, topks=topks)
+    mb.weight.data.copy_(wt)
+    tap = Tap(mb)
+    with torch.no_grad():
+        out_b = mb(qs, ks, vs)
+    ma = ref.QTAttA(nh, C // nh, topks=topks)
+    tap_a = Tap(ma)
+    with torch.no_grad():
+        out_a = ma(qs, ks, vs)
+    t = {f'q{i}': qs[i] for i in range(3)}
+    t.update({f'k{i}': ks[i] for i in range(3)})
+    t.update({f'v{i}': vs[i] for i in range(3)})
+    save('qtatt', weight=wt, topks=torch.tensor(topks), nhead=torch.tensor(nh), out_b=out_b, out_a=out_a,
+         b_idx0=tap.idx[0], b_idx1=tap.idx[1], a_idx0=tap_a.idx[0], a_idx1=tap_a.idx[1],
+         a_score0=tap_a.score[0], a_score1=tap_a.score[1], **t)
+
+
+def gen_cascade_qtatt(ref):
+    nh, C, h, w = 2, 64, 16, 16
+    d = synth.cascade_inputs(2, C, h, w, seed=102)
+    g = torch.Generator().manual_seed(7)
+    v = torch.randn(2, C, h, w, generator=g)
+    rp = torch.randn(2, nh, h * w, 100, generator=g)
+    m = ref.CascadeQTAttB(nh, C // nh, dilated=1)
+    with torch.no_grad():
+        msg, up = m(d['feat0'], d['feat1'], v, d['topk_pos01'], None)
+        msg_rp, _ = m(d['feat0'], d['feat1'], v, d['topk_pos01'], rp)
+    save('cascade_qtatt', query=d['feat0'], key=d['feat1'], value=v, topk_pos=d['topk_pos01'], rel_pos=rp,
+         nhead=torch.tensor(nh), message=msg, message_rel=msg_rp, upsampled_idx=up)
+
+
+def gen_cascade_match(ref):
+    B, C, h, w = 2, 32, 16, 16
+    hp, wp = h // 2, w // 2
+    cases = {}
+    for tag, pad, nms, thr in (('nms', False, True, 0.2), ('pad', True, True, 0.2), ('thr', False, False, 0.2), ('empty', False, True, 2.0)):
+        d = synth.cascade_inputs(B, C, h, w, seed=103, pad=pad)
+        m = ref.CascadeQTAttB(1, C, dilated=1)   # only used for its window-index expansion (upsampled_idx)
+        with torch.no_grad():
+            z = torch.zeros(B, C, h, w)
+            idx01 = m(z, z, z, d['topk_pos01'], None)[1]
+            idx10 = m(z, z, z, d['topk_pos10'], None)[1]
+        f0 = d['feat0'].flatten(2).transpose(1, 2).contiguous()
+        f1 = d['feat1'].flatten(2).transpose(1, 2).contiguous()
+        g = torch.Generator().manual_seed(8)
+        data = {'hw0_i': (h * 4, w * 4), 'hw1_i': (h * 4, w * 4), 'hw0_4c': (h, w), 'hw1_4c': (h, w),
+                'hw0_8c': (hp, wp), 'hw1_8c': (hp, wp), 'bs': B, 'stage_8c': {'next_conf_c01': d['pre_conf01']}}
+        m0 = m1 = None
+        if pad:
+            data['mask_4c0'], data['mask_4c1'] = d['mask0'], d['mask1']
+            m0, m1 = d['mask0'].flatten(1), d['mask1'].flatten(1)
+            data['scale0'] = torch.rand(B, 2, generator=g) + 0.5
+            data['scale1'] = torch.rand(B, 2, generator=g) + 0.5
+        cfg = {'thr': 0.0101, 'test_thr': thr, 'pre_thr': [0.2], 'border_rm': 2, 'double_check': True,
+               'train_pad_num_gt_min': 4096, 'match_type': 'softmax', 'dsmax_temperature': 1.0}
+        cas = {'propagation': 'window', 'dilated': 1, 'detector_mode': None, 'grid_size': 4,
+               'post_config': {'method': 'maxpool_nms' if nms else None, 'window_size': 5, 'topk': None, 'rt': None, 'rd': None}}
+        mod = ref.CascadeMatching(cfg, cas).eval()
+        with torch.no_grad():
+            mod(f0, f1, idx01, idx10, data, mask_c0=m0, mask_c1=m1, level='4c', pre_level='8c')
+        st = data['stage_4c']
+        if tag == 'nms':
+            cases.update(feat0=f0, feat1=f1, idx01=idx01, idx10=idx10, pre_conf=d['pre_conf01'],
+                         conf01=st['conf_matrix'], next_conf01=st['next_conf_c01'], next_conf10=st['next_conf_c10'],
+                         next_idx01=st['next_idx_c01'], next_idx10=st['next_idx_c10'])
+        if tag == 'pad':
+            cases.update(pad_mask0=d['mask0'], pad_mask1=d['mask1'], scale0=data['scale0'], scale1=data['scale1'],
+                         pad_next_conf01=st['next_conf_c01'], pad_next_idx01=st['next_idx_c01'], pad_next_idx10=st['next_idx_c10'])
+        for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0_c', 'mkpts1_c'):
+            cases[f'{tag}_{k}'] = st[k]
+    save('cascade_match', hw=torch.tensor([h, w]), **cases)
+
+
+def gen_fine(ref):
+    M = 24
+    f0, f1 = synth.fine_inputs(M, 25, 64, seed=104)
+    g = torch.Generator().manual_seed(9)
+    mk0, mk1 = torch.rand(M, 2, generator=g) * 100, torch.rand(M, 2, generator=g) * 100
+    b_ids = torch.randint(0, 2, (M,), generator=g)
+    sc1 = torch.rand(2, 2, generator=g) + 0.5
+    out = {}
+    for tag, extra in (('plain', {}), ('scaled', {'scale0': sc1, 'scale1': sc1})):
+        data = {'hw0_i': (128, 128), 'hw0_f': (64, 64), **extra,
+                'stage_4c': {'mkpts0_c': mk0, 'mkpts1_c': mk1, 'mconf': torch.rand(M), 'b_ids': b_ids}}
+        mod = ref.CascadeFineMatching('4c').eval()
+        with torch.no_grad():
+            mod(f0, f1, data)
+        out[f'{tag}_expec_f'], out[f'{tag}_mkpts1_f'] = data['expec_f'], data['mkpts1_f']
+    save('fine_match', feat_f0=f0, feat_f1=f1, mkpts1_c=mk1, b_ids=b_ids, scale1=sc1, **out)
+
+
+def gen_windows(ref):
+    """get_window_warp_idx of the reference's CascadeFeatureTransformer, called unbound on a stand-in object
+    (constructing the whole transformer needs modules outside the hot path)."""
+    tr = __import__('src.model.modules.transformer', fromlist=['CascadeFeatureTransformer'])
+    prop = __import__('src.model.modules.propagations', fromlist=['get_propagations'])
+    window, full = prop.get_propagations({'propagation': 'window', 'window_size': 5, 'dilated': 1})
+
+    class Stand:
+        pass
+    s = Stand()
+    s.window, s.full_window = window, full
+    g = torch.Generator().manual_seed(10)
+    H, W = 9, 13
+    idx = torch.randint(0, H * W, (2, H * W), generator=g)
+    idx[0, :4] = torch.tensor([0, W - 1, (H - 1) * W, H * W - 1])      # corners: exercise the rigid border shift
+    pos, _ = tr.CascadeFeatureTransformer.get_window_warp_idx(s, idx, 2, H, W)
+    save('windows', idx=idx, hw=torch.tensor([H, W]), pos=pos)
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref = refload.load()
+    gen_qtatt(ref)
+    gen_cascade_qtatt(ref)
+    gen_cascade_match(ref)
+    gen_fine(ref)
+    gen_windows(ref)

@@ -1,0 +1,118 @@
+"""GPU parity: fused cascade matching, NMS + match extraction and fine matching vs the CPU oracle.
+Integer outputs (next_idx, masks, match lists) bit-exact; fp within 1e-3 abs (observed ~1e-6)."""
+import pytest
+import torch
+
+import casmtr_b200
+from casmtr_b200 import functional as F
+from casmtr_b200 import synth
+from oracle import cascade, fine, qtatt
+
+pytestmark = pytest.mark.gpu
+
+
+def _stage(B, C, h, w, seed, pad=False):
+    d = synth.cascade_inputs(B, C, h, w, seed=seed, pad=pad)
+    idx01 = qtatt.cascade_window_idx(d['topk_pos01'], h, w)
+    idx10 = qtatt.cascade_window_idx(d['topk_pos10'], h, w)
+    up = lambda c: qtatt.quad_to_raster(c.reshape(B, 1, -1, 1, 100).expand(B, 1, -1, 4, 100), h // 2, w // 2).reshape(B, h * w, 100).contiguous()
+    d['idx01'], d['idx10'] = up(idx01), up(idx10)
+    d['f0'] = d['feat0'].flatten(2).transpose(1, 2).contiguous()
+    d['f1'] = d['feat1'].flatten(2).transpose(1, 2).contiguous()
+    return d
+
+
+@pytest.mark.parametrize('B,C,h,w,pad', [(2, 128, 32, 32, False), (1, 64, 32, 48, False), (2, 128, 32, 32, True), (1, 256, 16, 16, False)])
+def test_cascade_match(dev, B, C, h, w, pad):
+    d = _stage(B, C, h, w, 31, pad)
+    m0 = d['mask0'].flatten(1) if pad else None
+    m1 = d['mask1'].flatten(1) if pad else None
+    ref = cascade.cascade_match(d['f0'], d['f1'], d['idx01'], d['idx10'], m0, m1, 1.0)
+    out = F.cascade_match_forward(d['f0'].to(dev), d['f1'].to(dev), d['idx01'].to(dev), d['idx10'].to(dev),
+                                  None if m0 is None else m0.to(dev), None if m1 is None else m1.to(dev), 1.0)
+    for t in ('01', '10'):
+        assert torch.equal(out['next_idx' + t].cpu(), ref['next_idx' + t])
+        assert (out['next_conf' + t].cpu() - ref['next_conf' + t]).abs().max() < 1e-5
+        assert (out['conf' + t].cpu() - ref['conf' + t]).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize('B,h,w,nms,pad,border,scales,thr', [
+    (2, 32, 32, 5, False, 2, False, 0.2),
+    (2, 32, 48, None, False, 1, False, 0.2),
+    (2, 32, 32, 5, True, 2, True, 0.2),
+    (1, 32, 32, 3, False, 0, False, 0.1),
+    (3, 16, 16, 5, False, 2, False, 2.0),       # nothing survives -> fallback keeps element 0 of every sample
+])
+def test_match_extract(dev, B, h, w, nms, pad, border, scales, thr):
+    d = _stage(B, 128, h, w, 41, pad)
+    o = cascade.cascade_match(d['f0'], d['f1'], d['idx01'], d['idx10'], None, None, 1.0)
+    g = torch.Generator().manual_seed(9)
+    s0 = torch.rand(B, 2, generator=g) + 0.5 if scales else None
+    s1 = torch.rand(B, 2, generator=g) + 0.5 if scales else None
+    kw = dict(test_thr=thr, border_rm=border, nms_window=nms, pre_thrs=[0.2], double_check=True)
+    ref = cascade.extract_matches(o['next_conf01'], o['next_idx01'], o['next_idx10'], (h, w), (h, w), (h * 4, w * 4),
+                                  pre_confs=[(d['pre_conf01'], h // 2, w // 2)],
+                                  pad_mask0=d.get('mask0'), pad_mask1=d.get('mask1'), scale0=s0, scale1=s1, **kw)
+    c = lambda t: None if t is None else t.to(dev)
+    out = F.match_extract(c(o['next_conf01']), c(o['next_idx01']), c(o['next_idx10']), (h, w), (h, w), (h * 4, w * 4),
+                          pre_confs=[(c(d['pre_conf01']), h // 2, w // 2)],
+                          pad_mask0=c(d.get('mask0')), pad_mask1=c(d.get('mask1')), scale0=c(s0), scale1=c(s1), **kw)
+    for k in ('b_ids', 'i_ids', 'j_ids', 'mask'):
+        assert torch.equal(out[k].cpu(), ref[k]), k
+    for k in ('mconf', 'mkpts0_c', 'mkpts1_c'):
+        assert torch.equal(out[k].cpu(), ref[k].to(torch.float32)), k
+    assert len(ref['b_ids']) > 0
+
+
+def test_nms_ties(dev):
+    """maxpool NMS on a heavily tied map: first maximum in row-major window order wins."""
+    conf = (torch.randint(0, 4, (3, 20 * 30)).float() / 4).contiguous()
+    ref = cascade.nms_mask(conf, 20, 30, 5, 0.1)
+    zeros = torch.zeros(3, 600, dtype=torch.int64, device=dev)
+    out = F.match_extract(conf.to(dev), zeros, zeros, (20, 30), (20, 30), (80, 120), test_thr=0.1, border_rm=0,
+                          nms_window=5, double_check=False)
+    assert torch.equal(out['mask'].cpu(), ref)
+
+
+def test_cascade_matching_module(dev):
+    """Module API: data dict in, data['stage_4c'] out, same keys as the reference."""
+    B, h, w = 2, 32, 32
+    d = _stage(B, 128, h, w, 51)
+    cfg = {'thr': 0.0101, 'test_thr': 0.2, 'pre_thr': [0.2], 'border_rm': 2, 'double_check': True,
+           'train_pad_num_gt_min': 4096, 'match_type': 'softmax', 'dsmax_temperature': 1.0}
+    cas = {'propagation': 'window', 'dilated': 1, 'detector_mode': None, 'grid_size': 4,
+           'post_config': {'method': 'maxpool_nms', 'window_size': 5, 'topk': None, 'rt': None, 'rd': None}}
+    mod = casmtr_b200.CascadeMatching(cfg, cas).eval()
+    data = {'hw0_i': (h * 4, w * 4), 'hw1_i': (h * 4, w * 4), 'hw0_4c': (h, w), 'hw1_4c': (h, w),
+            'hw0_8c': (h // 2, w // 2), 'hw1_8c': (h // 2, w // 2), 'bs': B,
+            'stage_8c': {'next_conf_c01': d['pre_conf01'].to(dev)}}
+    mod(d['f0'].to(dev), d['f1'].to(dev), d['idx01'].to(dev), d['idx10'].to(dev), data, level='4c', pre_level='8c')
+    o = cascade.cascade_match(d['f0'], d['f1'], d['idx01'], d['idx10'], None, None, 1.0)
+    ref = cascade.extract_matches(o['next_conf01'], o['next_idx01'], o['next_idx10'], (h, w), (h, w), (h * 4, w * 4),
+                                  test_thr=0.2, border_rm=2, nms_window=5, pre_confs=[(d['pre_conf01'], h // 2, w // 2)],
+                                  pre_thrs=[0.2], double_check=True)
+    st = data['stage_4c']
+    for k in ('b_ids', 'i_ids', 'j_ids'):
+        assert torch.equal(st[k].cpu(), ref[k])
+    assert torch.equal(st['mkpts0_c'].cpu(), ref['mkpts0_c'].float())
+    assert (st['conf_matrix'].cpu() - o['conf01']).abs().max() < 1e-5
+    assert torch.equal(data['m_bids'].cpu(), ref['b_ids'])
+
+
+@pytest.mark.parametrize('M,WW,C', [(1, 25, 64), (37, 25, 64), (1000, 25, 128), (5, 9, 32)])
+def test_fine_match(dev, M, WW, C):
+    f0, f1 = synth.fine_inputs(M, WW, C, seed=61)
+    mk = torch.rand(M, 2) * 100
+    ref_e, ref_k = fine.fine_match(f0, f1, mk, 2.0)
+    e, k = F.fine_match_forward(f0.to(dev), f1.to(dev), mk.to(dev), 2.0)
+    assert (e.cpu() - ref_e).abs().max() < 1e-5
+    assert (k.cpu() - ref_k).abs().max() < 1e-4
+
+
+def test_fine_matching_module_empty(dev):
+    mod = casmtr_b200.CascadeFineMatching('4c').eval()
+    data = {'hw0_i': (128, 128), 'hw0_f': (64, 64),
+            'stage_4c': {'mkpts0_c': torch.zeros(0, 2, device=dev), 'mkpts1_c': torch.zeros(0, 2, device=dev),
+                         'mconf': torch.zeros(0, device=dev), 'b_ids': torch.zeros(0, dtype=torch.long, device=dev)}}
+    mod(torch.zeros(0, 25, 64, device=dev), torch.zeros(0, 25, 64, device=dev), data)
+    assert data['expec_f'].shape == (0, 3)

@@ -1,0 +1,76 @@
+"""GPU parity: fused QTAttA / QTAttB / CascadeQTAttB (module API -> C ABI) vs the CPU oracle.
+Indices bit-exact (compared as sets per row: torch.topk tie/sort order is unspecified, the synthetic
+inputs have no near-ties), messages within 1e-3 abs (BASELINE.json tolerance; observed ~1e-6)."""
+import pytest
+import torch
+
+import casmtr_b200
+from casmtr_b200 import functional as F
+from casmtr_b200 import synth
+from oracle import qtatt
+
+from conftest import topk_sets_equal
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _cuda(lst, dev):
+    return [t.to(dev) for t in lst]
+
+
+@pytest.mark.parametrize('B,nh,h,w,topks', [
+    (1, 8, 32, 32, [32, 16, 8]),      # BASELINE cfg 1 (256x256)
+    (2, 4, 24, 40, [16, 8, 8]),       # rectangular, batch 2
+    (1, 8, 60, 80, [32, 16, 16]),     # BASELINE cfg 4 grid (640x480)
+    (1, 2, 16, 16, [8, 4, 2]),
+    (1, 8, 16, 16, [4, 4]),           # two levels
+    (1, 8, 8, 8, [16]),               # single (dense) level
+])
+def test_qtatt_b(dev, B, nh, h, w, topks):
+    lv = len(topks)
+    qs, ks, vs, wt = synth.qtatt_inputs(B, nh * 32, h, w, lv, seed=11)
+    ref, aux = qtatt.qtatt_b(qs, ks, vs, wt, topks, nh, return_aux=True)
+    out, tk_idx, tk_sc = F.qtatt_forward(_cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev), topks, nh,
+                                         weight=wt.to(dev), attn_type='B', return_topk=True)
+    for i, ti in enumerate(tk_idx):
+        assert topk_sets_equal(ti.cpu(), aux['topk_idx'][i]), f'top-k index set mismatch at level {i}'
+        assert (torch.sort(tk_sc[i].cpu(), dim=2)[0] - torch.sort(aux['topk_score'][i], dim=2)[0]).abs().max() < 1e-5
+    assert (out.cpu() - ref).abs().max() < TOL
+
+
+@pytest.mark.parametrize('B,nh,h,w,topks', [(1, 8, 32, 32, [32, 16, 8]), (2, 4, 16, 24, [8, 8, 4]), (1, 8, 16, 16, [8, 8])])
+def test_qtatt_a(dev, B, nh, h, w, topks):
+    lv = len(topks)
+    qs, ks, vs, _ = synth.qtatt_inputs(B, nh * 32, h, w, lv, seed=12)
+    ref, aux = qtatt.qtatt_a(qs, ks, vs, topks, nh, return_aux=True)
+    out, tk_idx, tk_sc = F.qtatt_forward(_cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev), topks, nh,
+                                         attn_type='A', return_topk=True)
+    for i, ti in enumerate(tk_idx):
+        assert topk_sets_equal(ti.cpu(), aux['topk_idx'][i]), f'top-k index set mismatch at level {i}'
+    assert (out.cpu() - ref).abs().max() < TOL
+
+
+def test_qtatt_b_module_state_dict(dev):
+    m = casmtr_b200.QTAttB(8, 32, scale=3, topks=[32, 16, 8]).to(dev)
+    assert list(m.state_dict().keys()) == ['weight']
+    qs, ks, vs, wt = synth.qtatt_inputs(1, 256, 32, 32, 3, seed=13)
+    m.load_state_dict({'weight': wt})
+    with torch.no_grad():
+        out = m(_cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev))
+    assert out.shape == (1, 1024, 8, 32)
+    assert (out.cpu() - qtatt.qtatt_b(qs, ks, vs, wt, [32, 16, 8], 8)).abs().max() < TOL
+
+
+@pytest.mark.parametrize('B,nh,h,w,rel,dil', [(2, 4, 16, 16, False, 1), (1, 4, 24, 32, True, 1), (1, 2, 16, 16, False, 2), (1, 4, 52, 52, False, 1)])
+def test_cascade_qtatt_b(dev, B, nh, h, w, rel, dil):
+    C = nh * 32
+    d = synth.cascade_inputs(B, C, h, w, seed=21)
+    g = torch.Generator().manual_seed(5)
+    v = torch.randn(B, C, h, w, generator=g)
+    rp = torch.randn(B, nh, h * w, 100, generator=g) if rel else None
+    ref_m, ref_i = qtatt.cascade_qtatt_b(d['feat0'], d['feat1'], v, d['topk_pos01'], rp, nh, dil)
+    m = casmtr_b200.CascadeQTAttB(nh, 32, dilated=dil)
+    out_m, out_i = m(d['feat0'].to(dev), d['feat1'].to(dev), v.to(dev), d['topk_pos01'].to(dev), None if rp is None else rp.to(dev))
+    assert torch.equal(out_i.cpu(), ref_i)                      # integer work: bit-exact
+    assert (out_m.cpu() - ref_m).abs().max() < TOL
