@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/s of the CasMTR coarse-to-fine matching hot path at 832x832 on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host cores
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, pairs sharded, NCCL
+
+Workload = BASELINE.json configs[1]: CasMTR-4c outdoor, 832x832, batch 1 per GPU: 12 QTAttB + 4 CascadeQTAttB +
+CascadeMatching (2 sparse correlations, softmax/argmax, 5x5 NMS, extraction) + CascadeFineMatching per pair
+(casmtr_b200/pipeline.py).  A step = one pass of that sequence over one batch of synthetic feature maps.
+
+  value      pairs/s with the step's inputs resident in HBM (every call has its own input buffers; one step
+             touches ~0.9 GB > the 126 MB L2, so nothing is served from a previous step's cache lines)
+  e2e        pairs/s through the same module API with the inputs in pinned HOST memory: H2D of every input
+             and D2H of the match list inside the timed region (copy stream overlapped with compute)
+  roofline   the dominant kernel: algorithmic bytes per launch / its mean device time, CUDA events recorded by
+             the library around each of its launches inside the timed region (casmtr_profile_*)
+  cpu_baseline  the CPU oracle (a port of the reference algorithm, oracle/) timed on this host's cores on a
+             bounded sample: ONE full-size call of each kind, scaled by the per-pair call counts
+
+Prints ONE JSON line (rank 0).  The only place this file touches oracle/ is the cpu_baseline / --impl reference leg.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'image_pairs_per_sec_832x832_hot_path'
+UNIT = 'pairs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=832, help='square image size (multiple of 32)')
+    ap.add_argument('--pairs', type=int, default=1, help='image pairs per GPU per step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='wall-clock bound of the reference arm')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.rows, self.proc = [], None
+        sel = str(device_index)
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            sel = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+        except Exception:
+            pass
+        self.cmd = ['nvidia-smi', '-i', sel, f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100']
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()               # the exact process we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(smax), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_sample(wl, host, threads):
+    """One full-size call of each kind through the CPU oracle (reference algorithm, torch CPU fp32, all host
+    threads); returns (pairs_per_s extrapolated with the per-pair call counts, seconds spent, detail dict)."""
+    from oracle import cascade as ocas, fine as ofine, qtatt as oqt       # the checker, used here as the CPU baseline
+    torch.set_num_threads(threads)
+    t = {}
+    with torch.no_grad():
+        c = host['qt'][0]
+        t0 = time.perf_counter()
+        oqt.qtatt_b(c['q'], c['k'], c['v'], c['weight'], wl.topks, wl.nh8)
+        t['qtatt_b'] = time.perf_counter() - t0
+        c = host['cas'][0]
+        t0 = time.perf_counter()
+        _, idx01 = oqt.cascade_qtatt_b(c['q'], c['k'], c['v'], c['topk_pos'], None, wl.nh4)
+        t['cascade_qtatt_b'] = time.perf_counter() - t0
+        c1 = host['cas'][1]
+        idx10 = oqt.quad_to_raster(oqt.cascade_window_idx(c1['topk_pos'], wl.h4, wl.w4).reshape(wl.B, 1, -1, 1, 100)
+                                   .expand(wl.B, 1, -1, 4, 100), wl.h4 // 2, wl.w4 // 2).reshape(wl.B, wl.h4 * wl.w4, 100).contiguous()
+        m = host['match']
+        t0 = time.perf_counter()
+        o = ocas.cascade_match(m['feat0'], m['feat1'], idx01, idx10, None, None, 1.0)
+        r = ocas.extract_matches(o['next_conf01'], o['next_idx01'], o['next_idx10'], (wl.h4, wl.w4), (wl.h4, wl.w4), (wl.H, wl.W),
+                                 test_thr=0.2, border_rm=2, nms_window=5, pre_confs=[(m['pre_conf'], wl.h8, wl.w8)],
+                                 pre_thrs=[0.2], double_check=True)
+        t['cascade_matching'] = time.perf_counter() - t0
+        M = min(r['mconf'].shape[0], host['fine']['feat_f0'].shape[0])
+        t0 = time.perf_counter()
+        ofine.fine_match(host['fine']['feat_f0'][:M], host['fine']['feat_f1'][:M], r['mkpts1_c'][:M].float(), wl.H / wl.hf)
+        t['fine_matching'] = time.perf_counter() - t0
+    per_batch = wl.qt_calls * t['qtatt_b'] + wl.cas_calls * t['cascade_qtatt_b'] + t['cascade_matching'] + t['fine_matching']
+    return wl.B / per_batch, sum(t.values()), {k: round(v, 4) for k, v in t.items()} | {'matches': int(M)}
+
+
+SAMPLE_DESC = ('one full-size call of each kind (QTAttB, CascadeQTAttB, CascadeMatching+NMS+extract, FineMatching) through the '
+               'CPU oracle, seconds per pair = 12*t_qt + 4*t_cas + t_match + t_fine')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    from casmtr_b200 import pipeline
+    wl = pipeline.Workload(args.size, args.size, pairs=args.pairs)
+    host = pipeline.make_host_inputs(wl, seed=1234)
+    threads = os.cpu_count() or 1
+    runs, t_start = [], time.perf_counter()
+    for it in range(args.warmup + args.steps):          # as many of the W+K samples as the wall-clock budget allows
+        elapsed = time.perf_counter() - t_start
+        if it > 0 and elapsed + elapsed / it > args.cpu_budget_s:
+            break
+        runs.append(cpu_reference_sample(wl, host, threads))
+    done_w = min(args.warmup, len(runs) - 1)             # the first ones are warm-up, at least one is timed
+    vals = [r[0] for r in runs[done_w:]]
+    done_k, detail = len(vals), runs[-1][2]
+    value = statistics.median(vals)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done_k, 'warmup': done_w,
+        'ms_per_step': 1000.0 * wl.B / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': config_dict(wl, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': SAMPLE_DESC,
+                         'seconds_per_call': detail},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': ('reference algorithm = CPU oracle port (torch CPU fp32, all host threads); the reference is Python + CUDA '
+                 'extensions and /root/reference does not exist on the GPU box; requested steps/warmup are cut to fit '
+                 f'--cpu-budget-s={args.cpu_budget_s:.0f}'),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_dict(wl, n_gpus):
+    return {'workload': wl.name, 'image': [wl.H, wl.W], 'pairs_per_gpu': wl.B, 'global_pairs': wl.B * n_gpus,
+            'calls_per_pair': {'QTAttB': wl.qt_calls, 'CascadeQTAttB': wl.cas_calls, 'CascadeMatching': 1, 'CascadeFineMatching': 1},
+            'topks': wl.topks, 'parallelism': f'pairs sharded over {n_gpus} GPU(s), all-gather of the match list',
+            'cache': 'inputs larger than L2 (per-call buffers, ~0.9 GB per step)'}
+
+
+# ---------------------------------------------------------------------------------------------- this repo's arm
+def run_ours(args):
+    import torch.distributed as dist
+    from casmtr_b200 import dist as cdist
+    from casmtr_b200 import functional as F
+    from casmtr_b200 import pipeline
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU leg)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_gpus = world
+
+    wl = pipeline.Workload(args.size, args.size, pairs=args.pairs)
+    host = pipeline.make_host_inputs(wl, seed=1234 + 1000 * rank, pin=not args.no_e2e)
+    hp = pipeline.HotPath(wl).to(dev)
+    hp.load_level_weights(host)
+    dev_in = pipeline.tree_map(lambda t: t.to(dev), host)
+    pair_offset = rank * wl.B
+
+    def step():
+        out = hp(dev_in)
+        if world > 1:
+            out = cdist.gather_matches(out, pair_offset)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    n_matches = int(out['mconf'].shape[0])
+
+    # ---- timed region: K steps, CUDA events on the launch stream, library event pairs around every kernel
+    sampler = ClockSampler(local)
+    F.profile_collect()
+    sync_all()
+    sampler.start()
+    l0 = F.launch_count()
+    F.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync_all()
+    F.profile_enable(False)
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = (F.launch_count() - l0) // args.steps
+    prof = F.profile_collect()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = wl.B * n_gpus / (ms_step / 1000.0)
+
+    # ---- e2e: same module path, inputs from pinned host memory, result read back
+    e2e = None
+    if not args.no_e2e:
+        runner = pipeline.HostFedRunner(hp, host, dev)
+        for _ in range(3):
+            runner.step()
+        sync_all()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            res = runner.step()
+            if world > 1:
+                cdist.gather_matches({k: v.to(dev) for k, v in res.items() if k != 'expec_f'}, pair_offset)
+        e1.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        e_ms = max(e0.elapsed_time(e1), wall_ms)         # the D2H read ends on the host: take the later clock
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {'value': wl.B * n_gpus / (e_ms / args.steps / 1000.0), 'unit': UNIT,
+               'h2d_bytes_per_step': int(runner.h2d_bytes), 'd2h_bytes_per_step': int(runner.d2h_bytes),
+               'ms_per_step': e_ms / args.steps}
+
+    # ---- per-kernel breakdown and the roofline of the dominant kernel
+    peak, peak_src = peaks()
+    kernel_ms = sum(ms for ms, _ in prof.values())
+    breakdown = []
+    for kind, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        if n == 0:
+            continue
+        per = ms / n
+        alg = wl.bytes_kernel(kind)
+        row = {'kind': kind, 'launches_per_step': n / args.steps, 'ms_per_launch': round(per, 5), 'share': round(ms / kernel_ms, 4)}
+        if alg:
+            row['alg_bytes_per_launch'] = alg
+            row['gbps'] = round(alg / per / 1e6, 1)
+            row['frac_of_hbm_peak'] = round(alg / per / 1e6 / peak, 4)
+        breakdown.append(row)
+    dom = next((r for r in breakdown if 'gbps' in r), None)
+    roofline = None
+    if dom:
+        roofline = {'bound': 'hbm', 'kernel': dom['kind'], 'achieved': dom['gbps'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': dom['frac_of_hbm_peak'], 'traffic': ncu_traffic(dom['kind']), 'peak_source': peak_src,
+                    'alg_bytes_per_launch': dom['alg_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch']}
+    qt_ms = sum(prof[k][0] for k in ('qt_coarse', 'qt_fine_mid', 'qt_fine_last')) / args.steps / wl.qt_calls
+    lay = prof['layout']
+    lay_per_launch = lay[0] / max(lay[1], 1)
+    qt_call_ms = qt_ms + lay_per_launch                    # one layout launch per QTAttB call
+    qtatt_call = {'alg_bytes': wl.bytes_qtatt_call(), 'ms': round(qt_call_ms, 5),
+                  'gbps': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6, 1),
+                  'frac_of_hbm_peak': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6 / peak, 4)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': config_dict(wl, n_gpus), 'e2e': e2e, 'gpu_launches': int(launches) * args.steps,
+        'gpu_launches_per_step': int(launches), 'clocks': clocks, 'roofline': roofline, 'qtatt_call_roofline': qtatt_call,
+        'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'breakdown': breakdown, 'matches_per_step': n_matches,
+    }
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        v, spent, detail = cpu_reference_sample(wl, host, os.cpu_count() or 1)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                'sample': SAMPLE_DESC, 'seconds_per_call': detail, 'seconds_spent': round(spent, 2)}
+    else:
+        line['cpu_baseline'] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def ncu_traffic(kind):
+    """dram bytes per launch of the kernel from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(kind)
+    return None
+
+
+if __name__ == '__main__':
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))

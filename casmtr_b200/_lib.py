@@ -10,6 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libcasmtr_b200.so')
 MAX_LEVELS = 4
+K_COUNT = 9           # CASMTR_K_COUNT
 
 c_float_p = C.c_void_p      # raw device addresses (tensor.data_ptr())
 c_i64_p = C.c_void_p
@@ -36,6 +37,10 @@ SIGNATURES = {
     'casmtr_version': (C.c_int, []),
     'casmtr_last_error_string': (C.c_char_p, []),
     'casmtr_device_info': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    'casmtr_launch_count': (C.c_uint64, []),
+    'casmtr_profile_enable': (C.c_int, [C.c_int]),
+    'casmtr_profile_collect': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    'casmtr_kernel_kind_name': (C.c_char_p, [C.c_int]),
     'casmtr_score5d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_value_agg_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_score3d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 5 + [C.c_void_p]),

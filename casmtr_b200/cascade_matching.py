@@ -86,7 +86,8 @@ class CascadeMatching(nn.Module):
             raise NotImplementedError('casmtr_b200.CascadeMatching implements the inference branch only')
         o = F.cascade_match_forward(feat_c0.to(torch.float32).contiguous(), feat_c1.to(torch.float32).contiguous(),
                                     idx_c01.contiguous(), idx_c10.contiguous(), mask_c0, mask_c1,
-                                    temperature=self.temperature, need_conf=self.store_conf_matrix)
+                                    temperature=self.temperature, need_conf=self.store_conf_matrix,
+                                    need_conf10=False)       # the reference keeps only conf_matrix01 (:155)
         data[f'stage_{level}'] = {
             'conf_matrix': o['conf01'], 'detector_matrix01': None,
             'next_conf_c01_topk': None, 'next_idx_c01_topk': None,

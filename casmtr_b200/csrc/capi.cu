@@ -15,7 +15,72 @@ void casmtr_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// ---- launch accounting + optional event-pair timing (see LaunchScope in common.cuh)
+#include <atomic>
+#include <mutex>
+#include <vector>
+namespace {
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_prof_on{0};
+struct ProfRec { int kind; cudaEvent_t start, stop; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
+const char *const g_kind_names[CASMTR_K_COUNT] = {"layout", "qt_coarse", "qt_fine_mid", "qt_fine_last", "cascade_att",
+                                                  "cascade_match", "extract", "fine_match", "ops"};
+}  // namespace
+
+void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    *slot = -1;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.kind = kind;
+    if (!g_prof_free.empty()) {
+        r.start = g_prof_free.back().first; r.stop = g_prof_free.back().second;
+        g_prof_free.pop_back();
+    } else if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaEventRecord(r.start, stream);
+    g_prof_recs.push_back(r);
+    *slot = (int)g_prof_recs.size() - 1;
+}
+
+void casmtr_prof_end(int slot, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot >= 0 && slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].stop, stream);
+}
+
 extern "C" {
+
+uint64_t casmtr_launch_count(void) { return g_launches.load(); }
+
+int casmtr_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return CASMTR_OK;
+}
+
+int casmtr_profile_collect(double *ms_by_kind, uint64_t *launches_by_kind) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (const ProfRec &r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.stop) != cudaSuccess || cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) {
+            casmtr_set_error("casmtr_profile_collect: %s", cudaGetErrorString(cudaGetLastError()));
+            g_prof_recs.clear();
+            return CASMTR_E_CUDA;
+        }
+        if (ms_by_kind) ms_by_kind[r.kind] += ms;
+        if (launches_by_kind) launches_by_kind[r.kind] += 1;
+        g_prof_free.emplace_back(r.start, r.stop);
+    }
+    g_prof_recs.clear();
+    return CASMTR_OK;
+}
+
+const char *casmtr_kernel_kind_name(int kind) { return kind >= 0 && kind < CASMTR_K_COUNT ? g_kind_names[kind] : "?"; }
 
 int casmtr_version(void) { return CASMTR_VERSION; }
 

@@ -141,6 +141,7 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
     const size_t rows = (size_t)p.B * p.L0 + (size_t)p.B * p.L1;
     if (rows == 0) return CASMTR_OK;
     const unsigned blocks = (unsigned)((rows + 7) / 8);
+    LaunchScope ls(CASMTR_K_CASCADE_MATCH, stream);
     if (p.C <= 128) cascade_match_kernel<1><<<blocks, 256, 0, stream>>>(p);
     else if (p.C <= 256) cascade_match_kernel<2><<<blocks, 256, 0, stream>>>(p);
     else cascade_match_kernel<4><<<blocks, 256, 0, stream>>>(p);

@@ -28,6 +28,18 @@ void casmtr_set_error(const char *fmt, ...);
         }                                                                           \
     } while (0)
 
+// ---- launch accounting / optional per-kernel timing (capi.cu).  Every kernel launch of the library sits in
+// a LaunchScope: it counts the launch and, when casmtr_profile_enable(1) is active, brackets it with a CUDA
+// event pair recorded on the launch stream so bench.py can attribute time per kernel kind inside its timed region.
+void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot);
+void casmtr_prof_end(int slot, cudaStream_t stream);
+struct LaunchScope {
+    int slot;
+    cudaStream_t stream;
+    LaunchScope(int kind, cudaStream_t s) : slot(-1), stream(s) { casmtr_prof_begin(kind, s, &slot); }
+    ~LaunchScope() { if (slot >= 0) casmtr_prof_end(slot, stream); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

@@ -233,8 +233,8 @@ int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01,
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "match_extract: workspace %zu < %zu bytes", workspace_bytes, ws.off);
     a.valid0 = a.valid1 = nullptr;
     if (d.pad_mask0 && d.pad_mask1 && d.border_rm > 0) {
-        valid_extent_kernel<<<d.B, 256, 0, stream>>>(d.pad_mask0, d.h0, d.w0, v0);
-        valid_extent_kernel<<<d.B, 256, 0, stream>>>(d.pad_mask1, d.h1, d.w1, v1);
+        { LaunchScope ls(CASMTR_K_EXTRACT, stream); valid_extent_kernel<<<d.B, 256, 0, stream>>>(d.pad_mask0, d.h0, d.w0, v0); }
+        { LaunchScope ls(CASMTR_K_EXTRACT, stream); valid_extent_kernel<<<d.B, 256, 0, stream>>>(d.pad_mask1, d.h1, d.w1, v1); }
         CASMTR_CHECK_LAUNCH("valid_extent_kernel");
         a.valid0 = v0; a.valid1 = v1;
     }
@@ -242,12 +242,12 @@ int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01,
         cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream);
         return CASMTR_OK;
     }
-    extract_mask_kernel<<<nb, BLK, 0, stream>>>(a);
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_mask_kernel<<<nb, BLK, 0, stream>>>(a); }
     CASMTR_CHECK_LAUNCH("extract_mask_kernel");
-    extract_scan_kernel<<<1, 1024, 0, stream>>>(a, nb, count_out);
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_scan_kernel<<<1, 1024, 0, stream>>>(a, nb, count_out); }
     CASMTR_CHECK_LAUNCH("extract_scan_kernel");
     EmitOut e{mask_out, b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, capacity};
-    extract_emit_kernel<<<nb, BLK, 0, stream>>>(a, e);
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_emit_kernel<<<nb, BLK, 0, stream>>>(a, e); }
     CASMTR_CHECK_LAUNCH("extract_emit_kernel");
     return CASMTR_OK;
 }

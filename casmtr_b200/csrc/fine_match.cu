@@ -59,6 +59,7 @@ int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, c
     CASMTR_REQUIRE(W * W == WW && WW <= 32 && W >= 2, CASMTR_E_UNSUPPORTED, "fine_match: window %d must be a square <= 32 (W in 2..5)", WW);
     CASMTR_REQUIRE(C % 4 == 0 && C > 0, CASMTR_E_UNSUPPORTED, "fine_match: C=%d must be a positive multiple of 4", C);
     if (M == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_FINE_MATCH, stream);
     fine_match_kernel<<<(M + 7) / 8, 256, 0, stream>>>(f0, f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, W, C);
     CASMTR_CHECK_LAUNCH("fine_match_kernel");
     return CASMTR_OK;

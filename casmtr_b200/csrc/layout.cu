@@ -44,6 +44,7 @@ int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
         total += ((jobs.job[i].C + 31) / 32) * ((jobs.job[i].HW + 31) / 32);
     }
     if (total == 0 || B == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
     transpose_jobs_kernel<<<dim3(total, B), 256, 0, stream>>>(jobs);
     CASMTR_CHECK_LAUNCH("transpose_jobs_kernel");
     return CASMTR_OK;
@@ -70,6 +71,7 @@ int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, flo
     if (total == 0) return CASMTR_OK;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
     topk_to_api_kernel<<<blocks, 256, 0, stream>>>(idx, score, idx_out, score_out, n_tok, nh, k);
     CASMTR_CHECK_LAUNCH("topk_to_api_kernel");
     return CASMTR_OK;

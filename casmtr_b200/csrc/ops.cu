@@ -124,6 +124,7 @@ int launch_score5d(const float *q, const float *key, const int64_t *idx, float *
         cudaError_t e = cudaFuncSetAttribute(score5d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
     }
+    LaunchScope ls(CASMTR_K_OPS, stream);
     score5d_kernel<<<(unsigned)((size_t)B * N1), 128, smem, stream>>>(q, key, idx, out, N1, N2, H, D, K);
     CASMTR_CHECK_LAUNCH("score5d_kernel");
     return CASMTR_OK;
@@ -135,6 +136,7 @@ int launch_value_agg(const float *score, const float *value, const int64_t *idx,
     if (total == 0) return CASMTR_OK;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
+    LaunchScope ls(CASMTR_K_OPS, stream);
     value_agg_kernel<<<(unsigned)blocks, 256, 0, stream>>>(score, value, idx, out, total, N, K, H, M, D);
     CASMTR_CHECK_LAUNCH("value_agg_kernel");
     return CASMTR_OK;
@@ -144,6 +146,7 @@ int launch_score3d(const float *q, const float *key, const int64_t *idx, float *
                    int B, int N1, int N2, int C, int K, cudaStream_t stream) {
     const size_t rows = (size_t)B * N1;
     if (rows == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_OPS, stream);
     score3d_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(q, key, idx, out, rows, N1, N2, C, K);
     CASMTR_CHECK_LAUNCH("score3d_kernel");
     return CASMTR_OK;

@@ -275,6 +275,7 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((p.Sq + ROWS - 1) / ROWS, p.B * p.nh);
+    LaunchScope ls(CASMTR_K_QT_COARSE, stream);
     qtatt_coarse_kernel<<<grid, 128, smem, stream>>>(p, coarse_s_ld(p.Sk));
     CASMTR_CHECK_LAUNCH("qtatt_coarse_kernel");
     return CASMTR_OK;

@@ -257,6 +257,7 @@ int launch_t(const FineParams &p, cudaStream_t stream) {
     const long long blocks = (items + WARPS - 1) / WARPS;
     CASMTR_REQUIRE(blocks <= 0x7fffffffLL, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
     if (blocks == 0) return CASMTR_OK;
+    LaunchScope ls(CASCADE ? CASMTR_K_CASCADE_ATT : (DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST), stream);
     quad_attention_kernel<T, CASCADE, TYPE_A, DO_TOPK><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(p);
     CASMTR_CHECK_LAUNCH("quad_attention_kernel");
     return CASMTR_OK;

@@ -35,6 +35,25 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# ------------------------------------------------------------------------------------- launch accounting
+def launch_count():
+    """Kernels launched by libcasmtr_b200.so in this process so far."""
+    return int(lib().casmtr_launch_count())
+
+
+def profile_enable(on=True):
+    """Bracket every kernel launch of the library with a CUDA event pair on its launch stream."""
+    check(lib().casmtr_profile_enable(1 if on else 0), 'casmtr_profile_enable')
+
+
+def profile_collect():
+    """-> {kind_name: (device_ms, launches)} accumulated since the last collect (synchronises)."""
+    ms = (C.c_double * _lib.K_COUNT)()
+    n = (C.c_uint64 * _lib.K_COUNT)()
+    check(lib().casmtr_profile_collect(ms, n), 'casmtr_profile_collect')
+    return {lib().casmtr_kernel_kind_name(i).decode(): (ms[i], int(n[i])) for i in range(_lib.K_COUNT)}
+
+
 # ------------------------------------------------------------------------------------- op-level
 def score5d(query, key, index):
     """[B,N1,4,H,D] x [B,N2,H,D] gathered by index [B,N1,K,H] -> [B,N1,4,K,H]."""
@@ -166,9 +185,13 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
 
 
 # ------------------------------------------------------------------------------------- cascade matching
-def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, temperature=1.0, need_conf=True):
+def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, temperature=1.0, need_conf=True,
+                          need_conf10=None):
     """Fused sparse correlation + softmax + argmax, both directions.  Returns dict with conf01/conf10
-    (None unless need_conf), next_conf01/10 [B,L] fp32, next_idx01/10 [B,L] int64."""
+    (None unless need_conf / need_conf10; need_conf10 defaults to need_conf), next_conf01/10 [B,L] fp32,
+    next_idx01/10 [B,L] int64."""
+    if need_conf10 is None:
+        need_conf10 = need_conf
     _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
     _chk(idx01, 'idx01', torch.int64), _chk(idx10, 'idx10', torch.int64)
     B, L0, Cc = feat0.shape
@@ -180,7 +203,7 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
         m1 = _chk(mask1.reshape(B, L1).to(torch.uint8).contiguous(), 'mask1', torch.uint8)
     o = {
         'conf01': torch.empty(B, L0, K, dtype=torch.float32, device=dev) if need_conf else None,
-        'conf10': torch.empty(B, L1, K, dtype=torch.float32, device=dev) if need_conf else None,
+        'conf10': torch.empty(B, L1, K, dtype=torch.float32, device=dev) if need_conf10 else None,
         'next_conf01': torch.empty(B, L0, dtype=torch.float32, device=dev),
         'next_conf10': torch.empty(B, L1, dtype=torch.float32, device=dev),
         'next_idx01': torch.empty(B, L0, dtype=torch.int64, device=dev),

@@ -1,0 +1,254 @@
+"""The coarse-to-fine matching hot path of one CasMTR forward, as the sequence of module calls the
+reference model makes between its backbone and its match list (SURVEY.md §3.1, §8d "units of work"):
+
+    CasMTR-4c outdoor (reference src/model/cascade_model_stage3.py:139-178)
+      12 x QTAttB.forward            1/8 grid, C=256, 8 heads, topks [32,16,8]   (6 layers x 2 maps)
+       4 x CascadeQTAttB.forward     1/4 grid, C=128, 4 heads, 5x5 window -> K=100 (2 cross layers x 2 dirs)
+       1 x CascadeMatching.forward   1/4 grid: 2 sparse correlations + softmax/argmax + NMS(5) + extraction
+       1 x CascadeFineMatching.forward  [M,25,64] windows -> sub-pixel keypoints
+
+Everything between those calls in the reference (1x1 convs, MLPs, self-attention blocks, the
+backbone, F.unfold of the fine map) is out of scope, so the calls are fed with
+synthetic feature maps of the right shapes (casmtr_b200/synth.py).  bench.py, the full-size GPU
+tests and smoke() all drive the path through this one class, via the public module API.
+"""
+import torch
+import torch.nn as nn
+
+from . import synth
+from .cascade_matching import CascadeMatching
+from .fine_matching import CascadeFineMatching
+from .modules.quadtree_attention import CascadeQTAttB, QTAttB
+
+MATCH_CFG_4C_OUTDOOR = {        # configs/model_configs/outdoor/loftr_ds_quadtree_cas_twins_large_stage3.py via get_match_config(., 0)
+    'thr': 0.0101, 'test_thr': 0.2, 'pre_thr': [0.2], 'border_rm': 2, 'double_check': True,
+    'train_pad_num_gt_min': 4096, 'match_type': 'softmax', 'dsmax_temperature': 1.0}
+CAS_CFG_4C_OUTDOOR = {
+    'propagation': 'window', 'dilated': 1, 'detector_mode': None, 'grid_size': 4,
+    'post_config': {'method': 'maxpool_nms', 'window_size': 5, 'topk': None, 'rt': None, 'rd': None}}
+
+
+class Workload:
+    """Shapes of BASELINE.json configs[1] (CasMTR-4c outdoor) at a given square/rect image size."""
+
+    def __init__(self, height=832, width=832, pairs=1, qt_calls=12, cas_calls=4, topks=(32, 16, 8)):
+        assert height % 32 == 0 and width % 32 == 0, 'image size must be a multiple of 32 (1/8 grid with a 3-level pyramid)'
+        self.H, self.W, self.B = height, width, pairs
+        self.h8, self.w8 = height // 8, width // 8
+        self.h4, self.w4 = height // 4, width // 4
+        self.hf, self.wf = height // 2, width // 2
+        self.qt_calls, self.cas_calls, self.topks = qt_calls, cas_calls, list(topks)
+        self.C8, self.nh8, self.C4, self.nh4, self.Cf = 256, 8, 128, 4, 64
+        self.window, self.fine_ww = 5, 25
+        self.fine_cap = max(64, (self.h4 * self.w4 // 4)) * pairs         # windows pre-generated for FineMatching
+
+    @property
+    def name(self):
+        return f'CasMTR-4c outdoor {self.H}x{self.W} batch={self.B} per GPU, coarse->1/4 cascade + NMS + fine'
+
+    # ---- algorithmic (compulsory) bytes per CALL; fp32 features, int64 indices at the API edge
+    def bytes_qtatt_call(self):
+        L = [self.h8 * self.w8 // (4 ** i) for i in range(3)]
+        return 4 * self.C8 * (3 * sum(L) + L[0]) * self.B
+
+    def bytes_cascade_att_call(self):
+        L = self.h4 * self.w4
+        return (3 * L * self.C4 * 4 + (L // 4) * 25 * 2 * 8 + L * self.C4 * 4 + L * 100 * 8) * self.B
+
+    def bytes_cascade_match_call(self):
+        L = self.h4 * self.w4
+        return (2 * L * self.C4 * 4 + 2 * L * 100 * 8 + L * 100 * 4 + 2 * L * 12) * self.B
+
+    # ---- per-LAUNCH bytes of the individual kernels (DESIGN.md "kernels" table)
+    def bytes_kernel(self, kind):
+        L0, L1, L2 = [self.h8 * self.w8 // (4 ** i) for i in range(3)]
+        C, nh, B = self.C8, self.nh8, self.B
+        if kind == 'qt_fine_last':       # q,k,v,out at L0 + parent message at L1 + parent top-k list (int32)
+            return B * (4 * C * (4 * L0 + L1) + 4 * L1 * nh * self.topks[1])
+        if kind == 'qt_fine_mid':        # same at L1/L2, plus the emitted top-k (idx int32 + score fp32)
+            return B * (4 * C * (4 * L1 + L2) + 4 * L2 * nh * self.topks[0] + 8 * L1 * nh * self.topks[1])
+        if kind == 'qt_coarse':
+            return B * (4 * C * 4 * L2 + 8 * L2 * nh * self.topks[0])
+        if kind == 'cascade_att':
+            return self.bytes_cascade_att_call()
+        if kind == 'cascade_match':
+            return self.bytes_cascade_match_call()
+        return None
+
+
+def make_host_inputs(wl, seed=1234, pin=False):
+    """All inputs of one step (one batch of wl.B pairs) as CPU tensors, grouped per call."""
+    g = torch.Generator().manual_seed(seed)
+    B = wl.B
+    maybe_pin = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+    host = {'qt': [], 'cas': []}
+    for i in range(wl.qt_calls):
+        qs, ks, vs, wt = synth.qtatt_inputs(B, wl.C8, wl.h8, wl.w8, 3, seed=seed + 1 + i)
+        host['qt'].append({'q': [maybe_pin(t) for t in qs], 'k': [maybe_pin(t) for t in ks], 'v': [maybe_pin(t) for t in vs],
+                           'weight': wt})
+    c = synth.cascade_inputs(B, wl.C4, wl.h4, wl.w4, seed=seed + 100, max_shift=8)
+    for i in range(wl.cas_calls):
+        rev = i % 2 == 1                               # call order per cross layer: 0->1 then 1->0
+        q = (c['feat1'] if rev else c['feat0']) + 0.05 * torch.randn(B, wl.C4, wl.h4, wl.w4, generator=g)
+        k = (c['feat0'] if rev else c['feat1']) + 0.05 * torch.randn(B, wl.C4, wl.h4, wl.w4, generator=g)
+        v = torch.randn(B, wl.C4, wl.h4, wl.w4, generator=g)
+        host['cas'].append({'q': maybe_pin(q), 'k': maybe_pin(k), 'v': maybe_pin(v),
+                            'topk_pos': maybe_pin((c['topk_pos10'] if rev else c['topk_pos01']).contiguous())})
+    host['match'] = {'feat0': maybe_pin(c['feat0'].flatten(2).transpose(1, 2).contiguous()),
+                     'feat1': maybe_pin(c['feat1'].flatten(2).transpose(1, 2).contiguous()),
+                     'pre_conf': maybe_pin(c['pre_conf01'].contiguous())}
+    f0, f1 = synth.fine_inputs(wl.fine_cap, wl.fine_ww, wl.Cf, seed=seed + 200)
+    host['fine'] = {'feat_f0': maybe_pin(f0), 'feat_f1': maybe_pin(f1)}
+    return host
+
+
+def tree_map(fn, x):
+    if isinstance(x, torch.Tensor):
+        return fn(x)
+    if isinstance(x, dict):
+        return {k: tree_map(fn, v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [tree_map(fn, v) for v in x]
+    return x
+
+
+def tree_bytes(x):
+    n = [0]
+    tree_map(lambda t: n.__setitem__(0, n[0] + t.numel() * t.element_size()), x)
+    return n[0]
+
+
+class HotPath(nn.Module):
+    """The module sequence of one forward, built from the drop-in classes (reference constructors)."""
+
+    def __init__(self, wl):
+        super().__init__()
+        self.wl = wl
+        self.qt = nn.ModuleList([QTAttB(wl.nh8, wl.C8 // wl.nh8, scale=3, topks=wl.topks) for _ in range(wl.qt_calls)])
+        self.cas = nn.ModuleList([CascadeQTAttB(wl.nh4, wl.C4 // wl.nh4, dilated=1) for _ in range(wl.cas_calls)])
+        self.matching = CascadeMatching(MATCH_CFG_4C_OUTDOOR, CAS_CFG_4C_OUTDOOR, stage=1)
+        self.fine = CascadeFineMatching('4c')
+        self.eval()
+
+    def load_level_weights(self, host):
+        with torch.no_grad():
+            for m, call in zip(self.qt, host['qt']):
+                m.weight.copy_(call['weight'])
+
+    def data_dict(self, dev_in):
+        wl = self.wl
+        return {'bs': wl.B, 'hw0_i': (wl.H, wl.W), 'hw1_i': (wl.H, wl.W),
+                'hw0_8c': (wl.h8, wl.w8), 'hw1_8c': (wl.h8, wl.w8), 'hw0_4c': (wl.h4, wl.w4), 'hw1_4c': (wl.h4, wl.w4),
+                'hw0_f': (wl.hf, wl.wf), 'hw1_f': (wl.hf, wl.wf),
+                'stage_8c': {'next_conf_c01': dev_in['match']['pre_conf']}}
+
+    # the individual calls, so that a host-fed runner can interleave copies with them
+    def run_qt(self, i, call):
+        return self.qt[i](call['q'], call['k'], call['v'])
+
+    def run_cas(self, i, call):
+        return self.cas[i](call['q'], call['k'], call['v'], call['topk_pos'], None)
+
+    def run_match(self, dev_in, idx01, idx10):
+        data = self.data_dict(dev_in)
+        self.matching(dev_in['match']['feat0'], dev_in['match']['feat1'], idx01, idx10, data, level='4c', pre_level='8c')
+        return data
+
+    def run_fine(self, data, fine_in):
+        M = data['stage_4c']['mconf'].shape[0]
+        M = min(M, fine_in['feat_f0'].shape[0])
+        self.fine(fine_in['feat_f0'][:M], fine_in['feat_f1'][:M], data)
+        st = data['stage_4c']
+        return {'b_ids': st['b_ids'], 'i_ids': st['i_ids'], 'j_ids': st['j_ids'], 'mconf': st['mconf'],
+                'mkpts0': data['mkpts0_f'], 'mkpts1': data['mkpts1_f'], 'expec_f': data['expec_f']}
+
+    @torch.no_grad()
+    def forward(self, dev_in, keep=None):
+        """dev_in: make_host_inputs() moved to the GPU.  Returns the match list dict.  `keep`, if a dict, receives
+        the intermediate outputs (messages, upsampled indices, stage dict) for parity tests."""
+        idx = [None, None]
+        for i, call in enumerate(dev_in['qt']):
+            m = self.run_qt(i, call)
+            if keep is not None:
+                keep.setdefault('qt_msg', []).append(m)
+        for i, call in enumerate(dev_in['cas']):
+            m, up = self.run_cas(i, call)
+            idx[i % 2] = up
+            if keep is not None:
+                keep.setdefault('cas_msg', []).append(m)
+                keep.setdefault('cas_idx', []).append(up)
+        data = self.run_match(dev_in, idx[0], idx[1])
+        out = self.run_fine(data, dev_in['fine'])
+        if keep is not None:
+            keep['data'] = data
+        return out
+
+
+class HostFedRunner:
+    """End-to-end driver: the step's inputs start in (pinned) HOST memory.  A copy stream uploads each call's inputs
+    while the previous calls compute (per-call ready/consumed events), the match list is read back to the host."""
+
+    def __init__(self, hp, host, device):
+        self.hp, self.host, self.device = hp, host, device
+        self.dev = tree_map(lambda t: torch.empty_like(t, device=device), {k: host[k] for k in ('qt', 'cas', 'match')})
+        for d, h in zip(self.dev['qt'], host['qt']):
+            d['weight'] = h['weight'].to(device)
+        self.fine_dev = {k: torch.empty_like(v, device=device) for k, v in host['fine'].items()}
+        self.copy_stream = torch.cuda.Stream(device)
+        self.groups = [('qt', i) for i in range(len(host['qt']))] + [('cas', i) for i in range(len(host['cas']))] + [('match', None)]
+        self.ready = [torch.cuda.Event() for _ in self.groups]
+        self.consumed = [torch.cuda.Event() for _ in self.groups]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _pair(self, g):
+        kind, i = g
+        h = self.host[kind] if i is None else self.host[kind][i]
+        d = self.dev[kind] if i is None else self.dev[kind][i]
+        return h, d
+
+    def _upload(self, h, d):
+        n = 0
+        if isinstance(h, torch.Tensor):
+            d.copy_(h, non_blocking=True)
+            return h.numel() * h.element_size()
+        if isinstance(h, dict):
+            for k in h:
+                if k != 'weight':
+                    n += self._upload(h[k], d[k])
+            return n
+        for a, b in zip(h, d):
+            n += self._upload(a, b)
+        return n
+
+    @torch.no_grad()
+    def step(self):
+        main = torch.cuda.current_stream(self.device)
+        cs = self.copy_stream
+        h2d = 0
+        with torch.cuda.stream(cs):
+            for gi, g in enumerate(self.groups):
+                cs.wait_event(self.consumed[gi])            # the previous step's consumer of this buffer is done
+                h, d = self._pair(g)
+                h2d += self._upload(h, d)
+                self.ready[gi].record(cs)
+        idx = [None, None]
+        for gi, (kind, i) in enumerate(self.groups):
+            main.wait_event(self.ready[gi])
+            if kind == 'qt':
+                self.hp.run_qt(i, self.dev['qt'][i])
+            elif kind == 'cas':
+                _, up = self.hp.run_cas(i, self.dev['cas'][i])
+                idx[i % 2] = up
+            else:
+                data = self.hp.run_match(self.dev, idx[0], idx[1])      # host sync inside: the match count
+            self.consumed[gi].record(main)
+        M = min(data['stage_4c']['mconf'].shape[0], self.fine_dev['feat_f0'].shape[0])
+        for k in ('feat_f0', 'feat_f1'):                    # only the M windows the matches select
+            self.fine_dev[k][:M].copy_(self.host['fine'][k][:M], non_blocking=True)
+            h2d += M * self.host['fine'][k][0].numel() * 4
+        out = self.hp.run_fine(data, self.fine_dev)
+        res = {k: v.cpu() for k, v in out.items()}         # device -> host read of the result (synchronises)
+        self.h2d_bytes = h2d
+        self.d2h_bytes = tree_bytes(res)
+        return res

@@ -62,6 +62,30 @@ CASMTR_API const char *casmtr_last_error_string(void);
 /* SM count / L2 bytes of the current device (host-side helper for the bench harness). */
 CASMTR_API int casmtr_device_info(int *sm_count, size_t *l2_bytes);
 
+/* ---------------------------------------------------------------- launch accounting / kernel timing
+ * Kernel kinds, for the per-kernel breakdown of the bench harness (the reference's analogue is the
+ * named-region InferenceProfiler, src/utils/profiler.py:8-40). */
+enum {
+    CASMTR_K_LAYOUT = 0,        /* NCHW -> token-major transposes, top-k list export */
+    CASMTR_K_QT_COARSE = 1,     /* dense coarsest quadtree level */
+    CASMTR_K_QT_FINE_MID = 2,   /* intermediate quadtree levels (emit top-k) */
+    CASMTR_K_QT_FINE_LAST = 3,  /* finest quadtree level (merged message only) */
+    CASMTR_K_CASCADE_ATT = 4,   /* CascadeQTAttB window attention */
+    CASMTR_K_CASCADE_MATCH = 5, /* fused correlation + softmax + argmax */
+    CASMTR_K_EXTRACT = 6,       /* NMS / gates / scan / ordered emit */
+    CASMTR_K_FINE_MATCH = 7,
+    CASMTR_K_OPS = 8,           /* op-level drop-ins (score5d / value_agg / score3d) */
+    CASMTR_K_COUNT = 9
+};
+/* Total number of kernels this library has launched in this process (all threads). */
+CASMTR_API uint64_t casmtr_launch_count(void);
+/* on != 0: bracket every subsequent kernel launch with a CUDA event pair on its launch stream. */
+CASMTR_API int casmtr_profile_enable(int on);
+/* Synchronises the recorded events, ADDS per-kind device milliseconds / launch counts into the two
+ * HOST arrays (CASMTR_K_COUNT entries each; either may be NULL) and clears the record list. */
+CASMTR_API int casmtr_profile_collect(double *ms_by_kind, uint64_t *launches_by_kind);
+CASMTR_API const char *casmtr_kernel_kind_name(int kind);
+
 /* ---------------------------------------------------------------- op-level drop-ins (R1-R3) */
 
 /* out[b,n,f,k,h] = sum_d query[b,n,f,h,d] * key[b, index[b,n,k,h], h, d]
