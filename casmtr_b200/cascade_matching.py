@@ -87,7 +87,9 @@ class CascadeMatching(nn.Module):
         o = F.cascade_match_forward(feat_c0.to(torch.float32).contiguous(), feat_c1.to(torch.float32).contiguous(),
                                     idx_c01.contiguous(), idx_c10.contiguous(), mask_c0, mask_c1,
                                     temperature=self.temperature, need_conf=self.store_conf_matrix,
-                                    need_conf10=False)       # the reference keeps only conf_matrix01 (:155)
+                                    need_conf10=False,       # the reference keeps only conf_matrix01 (:155)
+                                    w0=data[f'hw0_{level}'][1] if f'hw0_{level}' in data else 0,
+                                    w1=data[f'hw1_{level}'][1] if f'hw1_{level}' in data else 0)
         data[f'stage_{level}'] = {
             'conf_matrix': o['conf01'], 'detector_matrix01': None,
             'next_conf_c01_topk': None, 'next_idx_c01_topk': None,

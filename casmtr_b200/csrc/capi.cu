@@ -27,7 +27,7 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof_recs;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 const char *const g_kind_names[CASMTR_K_COUNT] = {"layout", "qt_coarse", "qt_fine_mid", "qt_fine_last", "cascade_att",
-                                                  "cascade_match", "extract", "fine_match", "ops"};
+                                                  "cascade_match", "extract", "fine_match", "ops", "cascade_fallback"};
 }  // namespace
 
 void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot) {
@@ -150,12 +150,14 @@ static int check_qtatt_desc(const casmtr_qtatt_desc *d) {
 struct QtattBuffers {
     float *q[CASMTR_MAX_LEVELS], *k[CASMTR_MAX_LEVELS], *v[CASMTR_MAX_LEVELS];   // token-major, list order
     float *acc[CASMTR_MAX_LEVELS];                                                 // processing order
+    float *wsm;                                                                    // softmax of the level weights
     int *tk_idx[CASMTR_MAX_LEVELS];
     float *tk_sc[CASMTR_MAX_LEVELS];
 };
 
 static void carve_qtatt(const casmtr_qtatt_desc *d, Workspace &ws, QtattBuffers &bf) {
     const size_t C = (size_t)d->nhead * d->D;
+    bf.wsm = ws.take<float>(CASMTR_MAX_LEVELS);
     for (int l = 0; l < d->levels; ++l) {
         bf.q[l] = ws.take<float>((size_t)d->B * d->qh[l] * d->qw[l] * C);
         bf.k[l] = ws.take<float>((size_t)d->B * d->kh[l] * d->kw[l] * C);
@@ -216,7 +218,7 @@ int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
             CoarseParams cp;
             cp.q = bf.q[l]; cp.k = bf.k[l]; cp.v = bf.v[l];
             cp.acc = dst; cp.topk_idx = bf.tk_idx[0]; cp.topk_score = bf.tk_sc[0];
-            cp.level_weight = wts; cp.levels = d->levels;
+            cp.level_weight = wts; cp.levels = d->levels; cp.wsm = wts ? bf.wsm : nullptr;
             cp.B = d->B; cp.Sq = d->qh[l] * d->qw[l]; cp.Sk = d->kh[l] * d->kw[l];
             cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type;
             rc = launch_qtatt_coarse(cp, stream);
@@ -228,7 +230,7 @@ int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
             fp.acc_prev = bf.acc[i - 1]; fp.out = dst;
             fp.topk_idx = last ? nullptr : bf.tk_idx[i];
             fp.topk_score = last ? nullptr : bf.tk_sc[i];
-            fp.level_weight = wts; fp.levels = d->levels; fp.level = i;
+            fp.wsm = wts ? bf.wsm : nullptr; fp.level = i;
             fp.B = d->B; fp.nh = d->nhead;
             fp.h0 = d->qh[l]; fp.w0 = d->qw[l]; fp.h1 = d->kh[l]; fp.w1 = d->kw[l]; fp.w_prev = d->kw[l + 1];
             fp.kp = d->topks[i - 1]; fp.topk = d->topks[i]; fp.dil = 1;
@@ -253,6 +255,7 @@ size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1
     ws.take<float>((size_t)B * h0 * w0 * C);
     ws.take<float>((size_t)B * h1 * w1 * C);
     ws.take<float>((size_t)B * h1 * w1 * C);
+    ws.take<int>((size_t)B * (h0 / 2) * (w0 / 2) + 1);       // fallback cell list + count of the tile kernel
     return ws.off;
 }
 
@@ -273,6 +276,7 @@ int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *
     float *qt = ws.take<float>((size_t)B * h0 * w0 * C);
     float *kt = ws.take<float>((size_t)B * h1 * w1 * C);
     float *vt = ws.take<float>((size_t)B * h1 * w1 * C);
+    int *fb = ws.take<int>((size_t)B * (h0 / 2) * (w0 / 2) + 1);
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "cascade_qtatt: workspace %zu < %zu bytes", workspace_bytes, ws.off);
     TransposeJobs jobs;
     jobs.n = 3;
@@ -287,7 +291,14 @@ int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *
     fp.topk_pos = topk_pos; fp.rel_pos = rel_pos;
     fp.out = message; fp.upsampled_idx = upsampled_idx;
     fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1;
-    fp.kp = k; fp.dil = dilated; fp.levels = 1;
+    fp.kp = k; fp.dil = dilated;
+    if (k == 25 && dilated == 1) {
+        // regular 5x5 windows: TMA-tiled kernel for the coherent cells, gather kernel for the listed outliers
+        int *fb_count = fb + (size_t)B * (h0 / 2) * (w0 / 2);
+        rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, rel_pos, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
+        if (rc != CASMTR_OK) return rc;
+        fp.item_list = fb; fp.item_count = fb_count;
+    }
     return launch_quad_attention(fp, stream);
 }
 
@@ -297,7 +308,9 @@ int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
                              const uint8_t *mask0, const uint8_t *mask1, float temperature,
                              float *conf01, float *next_conf01, int64_t *next_idx01,
                              float *conf10, float *next_conf10, int64_t *next_idx10,
-                             int B, int L0, int L1, int C, int K, casmtr_stream_t stream) {
+                             int B, int L0, int L1, int C, int K, int w0, int w1, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(w0 >= 0 && w1 >= 0 && (w0 == 0 || L0 % w0 == 0) && (w1 == 0 || L1 % w1 == 0), CASMTR_E_INVALID,
+                   "cascade_match: grid widths %d / %d do not divide L0=%d / L1=%d", w0, w1, L0, L1);
     CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0 && K > 0, CASMTR_E_INVALID, "cascade_match: bad sizes");
     CASMTR_REQUIRE(feat0 && feat1 && idx01 && idx10 && next_conf01 && next_idx01 && next_conf10 && next_idx10,
                    CASMTR_E_INVALID, "cascade_match: null pointer");
@@ -308,7 +321,7 @@ int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
     p.inv_scale = 1.0f / ((float)C * temperature);
     p.conf01 = conf01; p.conf10 = conf10; p.next_conf01 = next_conf01; p.next_conf10 = next_conf10;
     p.next_idx01 = next_idx01; p.next_idx10 = next_idx10;
-    p.B = B; p.L0 = L0; p.L1 = L1; p.C = C; p.K = K;
+    p.B = B; p.L0 = L0; p.L1 = L1; p.C = C; p.K = K; p.w0 = w0; p.w1 = w1;
     return launch_cascade_match(p, (cudaStream_t)stream);
 }
 

@@ -5,9 +5,17 @@
 // which runs fast_score_computation (cuda_imp/score_cuda/src/score_computation_kernel.cu:23-40) twice
 // and ~10 elementwise / reduction torch ops over the [B,L,K] volume per direction.
 //
-// One warp = one query token of one direction.  A candidate's key row (C floats) is read
-// coalesced by the whole warp; partial dots of 8 candidates are combined with a transposing
-// butterfly, leaving candidate 8c + (lane>>2) of chunk c in every lane (replicated x4).
+// Two kernels:
+//  * cell kernel (grid shapes known and even, C = 128 or 64): one warp = the 2x2 sibling queries of one
+//    parent cell.  In the cascade the candidate lists come from CascadeQTAttB's upsampled_idx, which is the
+//    parent's window repeated for its 4 children (reference quadtree_attention.py:450), so the 4 index rows
+//    are identical: the warp verifies that (it has to read the rows anyway), then gathers every candidate
+//    key row ONCE -- 4x less L2->SM traffic, which is what bounds this kernel -- with cp.async (all K row
+//    gathers of the cell in flight at once, each a coalesced full row) into a chunk-swizzled smem slab, and
+//    computes with lane = candidate: conflict-free row reads, q chunks broadcast and shared by the candidate
+//    rounds (8 LDS.128 per 64 FMAs per lane), no shuffles until the softmax.  If the rows differ the warp
+//    falls back to the row algorithm for its 4 queries -- same results either way.
+//  * row kernel (no grid information, odd grids, other C): one warp = one query row, register gathers.
 // HBM traffic: features once (re-reads of key rows hit L2), idx once, conf (optional) once.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -16,22 +24,40 @@ namespace {
 
 constexpr int MAX_CHUNKS = 16;   // K <= 128
 
+struct Dir {                     // one matching direction as seen by a warp
+    const float *qf, *kf;        // query / key features
+    const int64_t *idx;
+    const uint8_t *mq, *mk;
+    float *conf, *next_conf;
+    int64_t *next_idx;
+    int Lq, Lk;
+};
+
+__device__ __forceinline__ Dir direction(const MatchParams &p, bool rev) {
+    Dir d;
+    d.qf = rev ? p.feat1 : p.feat0; d.kf = rev ? p.feat0 : p.feat1;
+    d.idx = rev ? p.idx10 : p.idx01;
+    d.mq = rev ? p.mask1 : p.mask0; d.mk = rev ? p.mask0 : p.mask1;
+    d.conf = rev ? p.conf10 : p.conf01;
+    d.next_conf = rev ? p.next_conf10 : p.next_conf01;
+    d.next_idx = rev ? p.next_idx10 : p.next_idx01;
+    d.Lq = rev ? p.L1 : p.L0; d.Lk = rev ? p.L0 : p.L1;
+    return d;
+}
+
+__device__ __forceinline__ long long clamp_idx(long long i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+
+__device__ __forceinline__ float dot4acc(const float4 a, const float4 b, float acc) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+// ---- one query row per warp.  Every score ends up replicated in 4 lanes (candidate = lane>>2).
 template <int NQ>
-__global__ void __launch_bounds__(256) cascade_match_kernel(MatchParams p) {
-    const int lane = threadIdx.x & 31;
-    size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const size_t rows0 = (size_t)p.B * p.L0, rows1 = (size_t)p.B * p.L1;
-    if (row >= rows0 + rows1) return;
-    const bool rev = row >= rows0;               // direction 1 -> 0
-    if (rev) row -= rows0;
-    const int Lq = rev ? p.L1 : p.L0, Lk = rev ? p.L0 : p.L1;
-    const size_t b = row / Lq;
-    const float *q = (rev ? p.feat1 : p.feat0) + row * p.C;
-    const float *kb = (rev ? p.feat0 : p.feat1) + b * (size_t)Lk * p.C;
-    const int64_t *ix = (rev ? p.idx10 : p.idx01) + row * p.K;
-    const uint8_t *mq = rev ? p.mask1 : p.mask0;
-    const uint8_t *mk = rev ? p.mask0 : p.mask1;
-    float *conf = rev ? p.conf10 : p.conf01;
+__device__ __forceinline__ void match_row(const MatchParams &p, const Dir &d, size_t row, int lane) {
+    const size_t b = row / d.Lq;
+    const float *q = d.qf + row * p.C;
+    const float *kb = d.kf + b * (size_t)d.Lk * p.C;
+    const int64_t *ix = d.idx + row * p.K;
     const int K = p.K, c4 = p.C >> 2;
 
     float4 qv[NQ];
@@ -40,7 +66,7 @@ __global__ void __launch_bounds__(256) cascade_match_kernel(MatchParams p) {
         const int cc = lane + 32 * c;
         qv[c] = cc < c4 ? ldg4(q + 4 * cc) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const bool q_ok = mq ? (mq[row] != 0) : true;
+    const bool q_ok = d.mq ? (d.mq[row] != 0) : true;
     const int mine = lane >> 2;                  // candidate within a chunk this lane ends up holding
 
     float sc[MAX_CHUNKS];
@@ -54,16 +80,11 @@ __global__ void __launch_bounds__(256) cascade_match_kernel(MatchParams p) {
             for (int j = 0; j < 8; ++j) {
                 part[j] = 0.f;
                 if (k0 + j < K) {
-                    long long idx = __ldg(ix + k0 + j);
-                    idx = idx < 0 ? 0 : (idx >= Lk ? Lk - 1 : idx);
-                    const float *kr = kb + (size_t)idx * p.C;
+                    const float *kr = kb + (size_t)clamp_idx(__ldg(ix + k0 + j), d.Lk) * p.C;
 #pragma unroll
                     for (int c = 0; c < NQ; ++c) {
                         const int cc = lane + 32 * c;
-                        if (cc < c4) {
-                            const float4 kv = ldg4(kr + 4 * cc);
-                            part[j] = fmaf(qv[c].x, kv.x, fmaf(qv[c].y, kv.y, fmaf(qv[c].z, kv.z, fmaf(qv[c].w, kv.w, part[j]))));
-                        }
+                        if (cc < c4) part[j] = dot4acc(qv[c], ldg4(kr + 4 * cc), part[j]);
                     }
                 }
             }
@@ -88,10 +109,9 @@ __global__ void __launch_bounds__(256) cascade_match_kernel(MatchParams p) {
             s *= p.inv_scale;
             const int k = k0 + mine;
             if (k < K) {
-                if (mq) {                        // window mask (:108-112, :125)
-                    long long idx = __ldg(ix + k);
-                    idx = idx < 0 ? 0 : (idx >= Lk ? Lk - 1 : idx);
-                    if (!(q_ok && mk[b * Lk + idx] != 0)) s = -1e9f;
+                if (d.mq) {                      // window mask (:108-112, :125)
+                    const long long idx = clamp_idx(__ldg(ix + k), d.Lk);
+                    if (!(q_ok && d.mk[b * d.Lk + idx] != 0)) s = -1e9f;
                 }
                 sc[ch] = s;
             }
@@ -118,19 +138,181 @@ __global__ void __launch_bounds__(256) cascade_match_kernel(MatchParams p) {
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 4));
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 8));
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 16));
-    if (conf) {                                  // lane (mine, r) stores chunks r, r+4, ..: 32 consecutive k per store
+    if (d.conf) {                                // lane (mine, r) stores chunks r, r+4, ..: 32 consecutive k per store
         const int r = lane & 3;
 #pragma unroll
         for (int mI = 0; mI < MAX_CHUNKS / 4; ++mI) {
             const float v = r == 0 ? sc[4 * mI] : r == 1 ? sc[4 * mI + 1] : r == 2 ? sc[4 * mI + 2] : sc[4 * mI + 3];
             const int k = 32 * mI + 8 * r + mine;
-            if (k < K) conf[row * K + k] = v / sum;
+            if (k < K) d.conf[row * K + k] = v / sum;
         }
     }
     if (lane == 0) {
-        (rev ? p.next_conf10 : p.next_conf01)[row] = 1.0f / sum;     // exp(0) / sum
-        (rev ? p.next_idx10 : p.next_idx01)[row] = ix[arg];
+        d.next_conf[row] = 1.0f / sum;           // exp(0) / sum
+        d.next_idx[row] = ix[arg];
     }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(256) cascade_match_row_kernel(MatchParams p) {
+    const int lane = threadIdx.x & 31;
+    size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t rows0 = (size_t)p.B * p.L0, rows1 = (size_t)p.B * p.L1;
+    if (row >= rows0 + rows1) return;
+    const bool rev = row >= rows0;               // direction 1 -> 0
+    if (rev) row -= rows0;
+    const Dir d = direction(p, rev);
+    match_row<NQ>(p, d, row, lane);
+}
+
+// ---- the 2x2 sibling queries of one parent cell per warp, candidate rows staged in shared memory
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+
+__host__ __device__ inline int cell_slab_floats(int K, int C) { return (K + 4) * C; }
+
+// CH = 16-byte chunks per feature row (C / 4): 32 or 16.  lane = candidate in the compute phase.
+template <int CH>
+__global__ void __launch_bounds__(256) cascade_match_cell_kernel(MatchParams p, int warps_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int C = 4 * CH, RPI = 32 / CH;      // rows per cp.async instruction
+    constexpr int R = MAX_CHUNKS / 4;             // candidate rounds of 32
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    size_t cell = blockIdx.x * (size_t)warps_per_cta + warp;
+    const size_t cells0 = (size_t)p.B * (p.L0 >> 2), cells1 = (size_t)p.B * (p.L1 >> 2);
+    if (cell >= cells0 + cells1) return;
+    const bool rev = cell >= cells0;
+    if (rev) cell -= cells0;
+    const Dir d = direction(p, rev);
+    const int wq = rev ? p.w1 : p.w0;            // query grid width
+    const int wp = wq >> 1, cells_per = d.Lq >> 2;
+    const size_t b = cell / cells_per;
+    const int pc = (int)(cell - b * cells_per);
+    const int py = pc / wp, px = pc - py * wp;
+    const size_t row00 = b * d.Lq + (size_t)(2 * py) * wq + 2 * px;
+#define ROWQ(f) (row00 + (size_t)((f) >> 1) * wq + ((f) & 1))
+    const int K = p.K;
+
+    // candidate lists: lane holds entries lane, lane+32, .. of sibling 0 (= its candidates in the compute phase);
+    // siblings 1..3 must carry the same list
+    int cand[R];
+    bool same = true;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+        const int k = lane + 32 * m;
+        cand[m] = 0;
+        if (k < K) {
+            const long long i0 = __ldg(d.idx + ROWQ(0) * K + k);
+            same = same && i0 == __ldg(d.idx + ROWQ(1) * K + k) && i0 == __ldg(d.idx + ROWQ(2) * K + k) &&
+                   i0 == __ldg(d.idx + ROWQ(3) * K + k);
+            cand[m] = (int)clamp_idx(i0, d.Lk);
+        }
+    }
+    if (!__all_sync(FULL_MASK, same)) {           // arbitrary lists: per-row algorithm, identical results
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) match_row<(CH + 31) / 32>(p, d, ROWQ(f), lane);
+        return;
+    }
+
+    float *Ks = smem + (size_t)warp * cell_slab_floats(K, C);   // [K][C], 16-byte chunks XOR-swizzled by (row & 7)
+    float *Qs = Ks + (size_t)K * C;                              // [4][C]
+    const float *kb = d.kf + b * (size_t)d.Lk * C;
+    {   // stage the 4 query rows and the K candidate rows (every global read is a full coalesced row)
+        const int sub = lane / CH, ch = lane % CH;
+#pragma unroll
+        for (int f = sub; f < 4; f += RPI) cp_async16(Qs + f * C + 4 * ch, d.qf + ROWQ(f) * C + 4 * ch);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            if (32 * m < K) {
+#pragma unroll 4
+                for (int l = 0; l < 32; l += RPI) {
+                    const int ci = __shfl_sync(FULL_MASK, cand[m], l + sub);
+                    const int k = 32 * m + l + sub;
+                    if (k < K) cp_async16(Ks + (size_t)k * C + 4 * (ch ^ (k & 7)), kb + (size_t)ci * C + 4 * ch);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+    }
+
+    // correlation: lane = candidate 32r + lane; q chunks are broadcast reads shared by the rounds
+    float sc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) sc[r][f] = 0.f;
+    const float *krow[R];
+    int sw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int c = min(32 * r + lane, K - 1);  // rows past K re-read the last row; masked below
+        krow[r] = Ks + (size_t)c * C;
+        sw[r] = c & 7;
+    }
+#pragma unroll 2
+    for (int j = 0; j < CH; ++j) {
+        float4 qv[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + f * C + 4 * j);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (32 * r < K) {                     // warp-uniform
+                const float4 kv = *reinterpret_cast<const float4 *>(krow[r] + 4 * (j ^ sw[r]));
+#pragma unroll
+                for (int f = 0; f < 4; ++f) sc[r][f] = dot4acc(qv[f], kv, sc[r][f]);
+            }
+        }
+    }
+    // scale, window mask (:108-112, :125)
+    bool q_ok[4] = {true, true, true, true};
+    if (d.mq) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) q_ok[f] = d.mq[ROWQ(f)] != 0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool valid = 32 * r + lane < K;
+        const bool k_ok = (d.mq && valid) ? d.mk[b * d.Lk + cand[r]] != 0 : true;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float s = sc[r][f] * p.inv_scale;
+            if (d.mq && !(q_ok[f] && k_ok)) s = -1e9f;
+            sc[r][f] = valid ? s : -INFINITY;
+        }
+    }
+    // softmax over the K candidates, max / first arg-max, per sibling
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        float m = sc[0][f];
+#pragma unroll
+        for (int r = 1; r < R; ++r) m = fmaxf(m, sc[r][f]);
+        m = warp_max(m);
+        float sum = 0.f;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (sc[r][f] == m) arg = min(arg, 32 * r + lane);
+            sc[r][f] = exp_neg(sc[r][f] - m);
+            sum += sc[r][f];
+        }
+        sum = warp_sum(sum);
+        arg = __reduce_min_sync(FULL_MASK, arg);
+        const size_t row = ROWQ(f);
+        if (d.conf) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (32 * r + lane < K) d.conf[row * K + 32 * r + lane] = sc[r][f] / sum;
+        }
+        if (lane == 0) {
+            d.next_conf[row] = 1.0f / sum;        // exp(0) / sum
+            d.next_idx[row] = d.idx[row * K + arg];
+        }
+    }
+#undef ROWQ
 }
 
 }  // namespace
@@ -140,11 +322,32 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE(p.C % 4 == 0 && p.C >= 4 && p.C <= 512, CASMTR_E_UNSUPPORTED, "cascade_match: C=%d must be a multiple of 4, <= 512", p.C);
     const size_t rows = (size_t)p.B * p.L0 + (size_t)p.B * p.L1;
     if (rows == 0) return CASMTR_OK;
-    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    const bool quad = p.w0 > 0 && p.w1 > 0 && p.w0 % 2 == 0 && p.w1 % 2 == 0 && p.L0 % p.w0 == 0 && p.L1 % p.w1 == 0 &&
+                      (p.L0 / p.w0) % 2 == 0 && (p.L1 / p.w1) % 2 == 0 && (p.C == 128 || p.C == 64);
     LaunchScope ls(CASMTR_K_CASCADE_MATCH, stream);
-    if (p.C <= 128) cascade_match_kernel<1><<<blocks, 256, 0, stream>>>(p);
-    else if (p.C <= 256) cascade_match_kernel<2><<<blocks, 256, 0, stream>>>(p);
-    else cascade_match_kernel<4><<<blocks, 256, 0, stream>>>(p);
+    if (quad) {
+        const size_t per_warp = sizeof(float) * cell_slab_floats(p.K, p.C);
+        int wpc = (int)((113 * 1024) / per_warp);
+        wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+        const size_t smem = per_warp * wpc;
+        const unsigned blocks = (unsigned)((rows / 4 + wpc - 1) / wpc);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(cascade_match_cell_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+            attr_set = true;
+        }
+        if (p.C == 128) cascade_match_cell_kernel<32><<<blocks, wpc * 32, smem, stream>>>(p, wpc);
+        else cascade_match_cell_kernel<16><<<blocks, wpc * 32, smem, stream>>>(p, wpc);
+    } else {
+        const unsigned blocks = (unsigned)((rows + 7) / 8);
+        if (p.C <= 128) cascade_match_row_kernel<1><<<blocks, 256, 0, stream>>>(p);
+        else if (p.C <= 256) cascade_match_row_kernel<2><<<blocks, 256, 0, stream>>>(p);
+        else cascade_match_row_kernel<4><<<blocks, 256, 0, stream>>>(p);
+    }
     CASMTR_CHECK_LAUNCH("cascade_match_kernel");
     return CASMTR_OK;
 }

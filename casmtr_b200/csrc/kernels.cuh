@@ -24,6 +24,7 @@ struct CoarseParams {
     int *topk_idx;              // [B,Sq,nh,k] key index at this level
     float *topk_score;          // [B,Sq,nh,k]
     const float *level_weight;  // raw QTAttB.weight (device) or NULL
+    float *wsm;                 // [levels] out: softmax(level_weight), written once for the finer levels' kernels (NULL if no weights)
     int levels;
     int B, Sq, Sk, nh, topk;
     int type_a;
@@ -44,14 +45,22 @@ struct FineParams {
     int *topk_idx;              // [B, h0*w0, nh, k] or NULL (last level / cascade)
     float *topk_score;          // same shape, or NULL
     int64_t *upsampled_idx;     // [B, h0*w0, 4kp] or NULL (cascade)
-    const float *level_weight;  // raw weights or NULL
-    int levels, level;          // this level's position in the weight vector
+    const float *wsm;           // softmax(QTAttB.weight) written by the coarse kernel, or NULL (type A, cascade: weight 1)
+    int level;                  // this level's position in the weight vector
     int B, nh, h0, w0, h1, w1, w_prev;
     int kp, topk;               // candidates = 4*kp; topk selected for the next level
     int dil;                    // child offset dilation (cascade), 1 otherwise
     int type_a, final_level;
+    const int *item_list;       // NULL, or device list of cells (b * Np + parent) to process for every head (cascade fallback)
+    const int *item_count;      // device int: length of item_list
 };
 int launch_quad_attention(const FineParams &p, cudaStream_t stream);
+
+// ---- cascade_tile.cu: TMA-tiled CascadeQTAttB (k = 25, dilated = 1); cells it cannot serve go to fb_list
+size_t cascade_tile_smem_bytes();
+int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const float *rel_pos,
+                            float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
+                            int B, int nh, int h0, int w0, int h1, int w1, cudaStream_t stream);
 
 // ---- ops.cu
 int launch_score5d(const float *q, const float *key, const int64_t *idx, float *out,
@@ -71,6 +80,7 @@ struct MatchParams {
     float *next_conf01, *next_conf10;
     int64_t *next_idx01, *next_idx10;
     int B, L0, L1, C, K;
+    int w0, w1;                 // grid widths of image 0 / 1 (0 = unknown: one warp per query row)
 };
 int launch_cascade_match(const MatchParams &p, cudaStream_t stream);
 

@@ -3,31 +3,40 @@
 // Reference: QTAttB.process_coarse_level
 //   cuda_imp/QuadTreeAttention/QuadtreeAttention/modules/quadtree_attention.py:161-178
 // and QTAttA.process_coarse_level :25-44.  The reference materialises QK and A as [B,L,S,nh]
-// tensors in HBM and runs torch.topk on a strided dim; here a CTA keeps a 16 x S score slab
+// tensors in HBM and runs torch.topk on a strided dim; here a CTA keeps a ROWS x S score slab
 // in shared memory, so HBM sees only Q, K, V once (K/V re-reads hit L2) plus the outputs.
 //
-// One CTA = 16 query rows of one (batch, head); 128 threads.
-//   phase 1  S = scale * Q K^T   (4x4 register tiles, K streamed through a 128-token smem tile)
-//   phase 2  row softmax in smem
-//   phase 3  exact top-k per row (one warp per row): lane-local top-2 -> threshold by bitwise
-//            bisection with ballots -> compact survivors -> k rounds of warp arg-max
-//   phase 4  O = A V (V streamed through the same tile buffer), split over the 4 warps, reduced
+// One CTA = ROWS (32) query rows of one (batch, head); 256 threads.
+//   phase 1  S = scale * Q K^T.  lane = query row (its 32-float q row lives in registers), the K tile
+//            (64 tokens, cp.async double-buffered) is read with BROADCAST LDS.128: 8 LDS per 32 FMAs per
+//            lane and no bank conflicts; warp w owns tokens 8w..8w+7 of every tile.  The slab row stride
+//            is odd, so the per-lane score stores are conflict-free too.
+//   phase 2  row softmax in smem, one warp per row.
+//   phase 3  exact top-k per row, one warp per row, no serial selection loop:
+//            lane-local top-2 -> T = k-th largest of those 64 keys by rank counting (64 shuffles)
+//            -> compact the survivors {a >= T} (k <= n, typically n ~ 40) -> rank every survivor among
+//            the survivors by the same counting scheme; rank < k writes itself to slot `rank`, which
+//            yields the list sorted descending like torch.topk(sorted=True) (ties: lower key index first).
+//   phase 4  O = A V, lane = query row again (32 accumulators in registers), V tile broadcast from smem,
+//            warps split the tokens, partial sums reduced across warps through smem.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace {
 
-constexpr int ROWS = 16;        // query rows per CTA
-constexpr int TILE = 128;       // key/value tokens per smem tile
-constexpr int KV_LD = 36;       // padded row length of the tile (floats): conflict-free LDS.128
-constexpr int Q_LD = 36;
-constexpr int LIST_CAP = 256;   // survivor list capacity per warp
+constexpr int NW = 8;           // warps per CTA
+constexpr int TILE = 64;        // key/value tokens per smem tile
 constexpr int D = 32;
+constexpr int LIST_CAP = 64;    // survivor list capacity per warp (2 per lane)
+constexpr int RED_LD = 33;
 
 __device__ __forceinline__ unsigned key_of(float v) { return v >= 0.f ? __float_as_uint(v) + 1u : 0u; }
 
 // k rounds of warp arg-max over vals[0..n) (entries < 0 are dead).  Lane `it` ends up holding
 // the it-th largest (value, position-in-list).  Destroys the selected entries (sets them to -1).
+// Slow path, only used when a row has so many ties that more than LIST_CAP entries survive.
 __device__ __forceinline__ void warp_select_k(float *vals, int n, int k, int lane, float &res_val, int &res_j) {
     res_val = -1.f;
     res_j = -1;
@@ -50,13 +59,29 @@ __device__ __forceinline__ void warp_select_k(float *vals, int n, int k, int lan
     }
 }
 
-__global__ void __launch_bounds__(128) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
+// stage one K/V tile (TILE tokens x 32 floats of head h) into smem with 16-byte cp.async; rows past Sk are zero-filled
+__device__ __forceinline__ void load_tile_async(float *dst, const float *src_head, int tok0, int Sk, int C, int tid) {
+    for (int i = tid; i < TILE * 8; i += NW * 32) {
+        const int t = i >> 3, c = i & 7;
+        const int tok = tok0 + t;
+        float *d = dst + t * D + 4 * (c ^ (((t >> 2) & 1) << 2));     // 16-byte chunk swizzle: tokens t and t+4 (the two lane halves of a 16-row CTA) hit different banks
+        if (tok < Sk) __pipeline_memcpy_async(d, src_head + (size_t)tok * C + 4 * c, 16);
+        else *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __pipeline_commit();
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
+    constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16)
+    constexpr int TOK_PER_WARP = TILE / NW;        // 8
     extern __shared__ __align__(16) float smem[];
-    float *Ss = smem;                               // [ROWS][s_ld]
-    float *Qs = Ss + ROWS * s_ld;                   // [ROWS][Q_LD]
-    float *KVs = Qs + ROWS * Q_LD;                  // [TILE][KV_LD]   (aliased by the AV reduction)
-    float *lval = KVs + TILE * KV_LD;               // [4][LIST_CAP]
-    int *lpos = (int *)(lval + 4 * LIST_CAP);       // [4][LIST_CAP]
+    float *KVs = smem;                              // [2][TILE][D]
+    float *Ss = KVs + 2 * TILE * D;                 // [ROWS][s_ld]       (aliased by the AV reduction buffer)
+    const int slab_floats = ROWS * s_ld > NW * 32 * RED_LD ? ROWS * s_ld : NW * 32 * RED_LD;
+    float *lval = Ss + slab_floats;                 // [NW][LIST_CAP]
+    int *lpos = (int *)(lval + NW * LIST_CAP);      // [NW][LIST_CAP]
+    float *rsum = (float *)(lpos + NW * LIST_CAP);  // [32] row sums of exp
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y / p.nh, h = blockIdx.y % p.nh;
@@ -68,98 +93,85 @@ __global__ void __launch_bounds__(128) qtatt_coarse_kernel(CoarseParams p, int s
     const int n_tiles = (p.Sk + TILE - 1) / TILE;
     const int s_pad = n_tiles * TILE;
     const float scale = rsqrtf((float)D);           // 1/sqrt(32), same fp32 value as 1.0 / D ** 0.5
-
-    // ---- Q rows -> smem
-    for (int i = tid; i < ROWS * 8; i += 128) {
-        const int r = i >> 3, c = i & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < p.Sq) v = ldg4(qb + (size_t)(row0 + r) * C + 4 * c);
-        *reinterpret_cast<float4 *>(Qs + r * Q_LD + 4 * c) = v;
-    }
+    const int myrow = lane % ROWS, half = lane / ROWS;
+    const int grow = min(row0 + myrow, p.Sq - 1);   // clamped: out-of-range rows compute garbage that is never stored
 
     // ---- phase 1: scores
-    const int tx = lane, ty = warp;                 // tokens tx+32j, rows 4ty+i
+    load_tile_async(KVs, kb, 0, p.Sk, C, tid);
+    float4 q[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) q[c] = ldg4(qb + (size_t)grow * C + 4 * c);
     for (int kt = 0; kt < n_tiles; ++kt) {
+        float *cur = KVs + (kt & 1) * TILE * D;
+        if (kt + 1 < n_tiles) load_tile_async(KVs + ((kt + 1) & 1) * TILE * D, kb, (kt + 1) * TILE, p.Sk, C, tid);
+        else __pipeline_commit();
+        __pipeline_wait_prior(1);
         __syncthreads();
-        for (int i = tid; i < TILE * 8; i += 128) {
-            const int t = i >> 3, c = i & 7;
-            const int tok = kt * TILE + t;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tok < p.Sk) v = ldg4(kb + (size_t)tok * C + 4 * c);
-            *reinterpret_cast<float4 *>(KVs + t * KV_LD + 4 * c) = v;
-        }
-        __syncthreads();
-        float acc[4][4];
+        // warp w: tokens w*8 .. w*8+7 of the tile; with 16-row CTAs the two lane halves take 4 tokens each
+        constexpr int TPL = TOK_PER_WARP / HALVES;  // tokens per lane group
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int t0 = 0; t0 < TPL; t0 += 4) {
+            const int tb = warp * TOK_PER_WARP + half * TPL + t0;
+            float2 acc[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+            const int sw = ((tb >> 2) & 1) << 2;        // tb is a multiple of 4: the 4 tokens share the swizzle
 #pragma unroll
-        for (int dq = 0; dq < 8; ++dq) {
-            float4 qv[4], kv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4 *>(Qs + (4 * ty + i) * Q_LD + 4 * dq);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4 *>(KVs + (tx + 32 * j) * KV_LD + 4 * dq);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int c = 0; c < 8; ++c) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    acc[i][j] = fmaf(qv[i].x, kv[j].x, acc[i][j]);
-                    acc[i][j] = fmaf(qv[i].y, kv[j].y, acc[i][j]);
-                    acc[i][j] = fmaf(qv[i].z, kv[j].z, acc[i][j]);
-                    acc[i][j] = fmaf(qv[i].w, kv[j].w, acc[i][j]);
+                    const float4 kv = *reinterpret_cast<const float4 *>(cur + (tb + j) * D + 4 * (c ^ sw));
+                    acc[j] = __ffma2_rn(make_float2(q[c].x, q[c].y), make_float2(kv.x, kv.y), acc[j]);
+                    acc[j] = __ffma2_rn(make_float2(q[c].z, q[c].w), make_float2(kv.z, kv.w), acc[j]);
                 }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int tok = kt * TILE + tx + 32 * j;
-                Ss[(4 * ty + i) * s_ld + tok] = tok < p.Sk ? acc[i][j] * scale : -INFINITY;
+                const int tok = kt * TILE + tb + j;
+                Ss[myrow * s_ld + tok] = tok < p.Sk ? (acc[j].x + acc[j].y) * scale : -INFINITY;
             }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- phase 2 + 3: softmax and top-k, warp `warp` owns rows warp, warp+4, warp+8, warp+12
+    // ---- phase 2 + 3: softmax and top-k, warp `warp` owns rows warp, warp+NW, ...
     float *mylv = lval + warp * LIST_CAP;
     int *mylp = lpos + warp * LIST_CAP;
-    for (int rr = 0; rr < 4; ++rr) {
-        const int r = warp + 4 * rr;
+    for (int r = warp; r < ROWS; r += NW) {
         if (row0 + r >= p.Sq) continue;            // warp-uniform
         float *srow = Ss + r * s_ld;
         float m = -INFINITY;
         for (int e = lane; e < p.Sk; e += 32) m = fmaxf(m, srow[e]);
         m = warp_max(m);
+        // the slab keeps the UNNORMALISED exp(s - max): the order is the same, only the k selected scores and the
+        // A.V result are divided by the row sum (phase 4)
         float sum = 0.f;
-        for (int e = lane; e < p.Sk; e += 32) {
-            const float ex = exp_neg(srow[e] - m);
-            srow[e] = ex;
-            sum += ex;
-        }
-        sum = warp_sum(sum);
         float m1 = -1.f, m2 = -1.f;                 // lane-local two largest
         for (int e = lane; e < s_pad; e += 32) {
-            float a = 0.f;
+            float ex = 0.f;                         // padding columns become 0 for the AV tiles
             if (e < p.Sk) {
-                a = srow[e] / sum;
-                if (a > m1) { m2 = m1; m1 = a; } else if (a > m2) { m2 = a; }
+                ex = exp_neg(srow[e] - m);
+                sum += ex;
+                if (ex > m1) { m2 = m1; m1 = ex; } else if (ex > m2) { m2 = ex; }
             }
-            srow[e] = a;                            // padding columns become 0 for the AV tiles
+            srow[e] = ex;
         }
-        // threshold: largest T such that at least k of the 64 lane-top-2 keys are >= T
+        sum = warp_sum(sum);
+        if (lane == 0) rsum[r] = sum;
+        // T = k-th largest of the 64 lane-top-2 keys: a key's rank is the number of keys strictly above it;
+        // the k-th largest is the smallest key with rank < k.  At least k entries of the row are >= T.
         const unsigned k1 = key_of(m1), k2 = key_of(m2);
-        unsigned T = 0;
-        for (int bit = 31; bit >= 0; --bit) {
-            const unsigned cand = T | (1u << bit);
-            const int c = __popc(__ballot_sync(FULL_MASK, k1 >= cand)) + __popc(__ballot_sync(FULL_MASK, k2 >= cand));
-            if (c >= p.topk) {
-                T = cand;
-                if (c == p.topk) break;
-            }
+        int c1 = 0, c2 = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const unsigned a1 = __shfl_sync(FULL_MASK, k1, l), a2 = __shfl_sync(FULL_MASK, k2, l);
+            c1 += (a1 > k1) + (a2 > k1);
+            c2 += (a1 > k2) + (a2 > k2);
         }
+        const unsigned candT = c2 < p.topk ? k2 : (c1 < p.topk ? k1 : 0xffffffffu);
+        const unsigned T = __reduce_min_sync(FULL_MASK, candT);
         __syncwarp();
-        // compact survivors
+        // compact survivors {a >= T} in key order
         int n = 0;
         for (int e0 = 0; e0 < p.Sk; e0 += 32) {
             const int e = e0 + lane;
@@ -173,65 +185,79 @@ __global__ void __launch_bounds__(128) qtatt_coarse_kernel(CoarseParams p, int s
             }
         }
         __syncwarp();
-        float rv;
-        int rj, ridx = 0;
+        float rv = -1.f;
+        int ridx = 0;
         if (n <= LIST_CAP && n >= p.topk) {
-            warp_select_k(mylv, n, p.topk, lane, rv, rj);
-            if (lane < p.topk) ridx = mylp[rj];
+            // rank each survivor (2 per lane) among all survivors: descending value, ties by list position
+            // (= key index, the list is in key order); rank < k -> that lane owns output slot `rank`
+            const float va = lane < n ? mylv[lane] : -1.f, vb2 = lane + 32 < n ? mylv[lane + 32] : -1.f;
+            const unsigned ka = key_of(va), kb2 = key_of(vb2);
+            int ra = 0, rb = 0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const unsigned oa = __shfl_sync(FULL_MASK, ka, l), ob = __shfl_sync(FULL_MASK, kb2, l);
+                ra += (oa > ka || (oa == ka && l < lane)) + (ob > ka);
+                rb += (oa >= kb2) + (ob > kb2 || (ob == kb2 && l < lane));
+            }
+            __syncwarp();
+            // scatter (value, key index) to the slot given by the rank, then lane `slot` picks it up
+            const int pa = lane < n ? mylp[lane] : 0, pb = lane + 32 < n ? mylp[lane + 32] : 0;
+            __syncwarp();
+            if (lane < n && ra < p.topk) { mylv[ra] = va; mylp[ra] = pa; }
+            if (lane + 32 < n && rb < p.topk) { mylv[rb] = vb2; mylp[rb] = pb; }
+            __syncwarp();
+            if (lane < p.topk) { rv = mylv[lane]; ridx = mylp[lane]; }
         } else {                                    // massive ties: exact but slow path on the row itself
+            int rj;
             warp_select_k(srow, p.Sk, p.topk, lane, rv, rj);
             ridx = rj;
             __syncwarp();
-            if (lane < p.topk) srow[ridx] = rv;        // restore
+            if (lane < p.topk) srow[ridx] = rv;     // restore
         }
+        __syncwarp();
         if (lane < p.topk) {
             const size_t o = (((size_t)b * p.Sq + row0 + r) * p.nh + h) * p.topk + lane;
             p.topk_idx[o] = ridx;
-            p.topk_score[o] = rv;
+            p.topk_score[o] = rv / sum;
             if (p.type_a) srow[ridx] = 0.f;         // QTAttA: selected keys leave the message (:37-42)
         }
     }
     __syncthreads();
 
-    // ---- phase 4: O = A V.  lane = (rg, dq): rows rg+4i, dims 4dq..4dq+3; warp w takes tokens 32w.. of each tile
-    const int rg = lane >> 3, dq = lane & 7;
-    float o[4][4];
+    // ---- phase 4: O = A V.  lane = row, 32 output dims in registers; warp w takes tokens w*8.. of each tile
+    float2 o[D / 2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[i][c] = 0.f;
+    for (int d = 0; d < D / 2; ++d) o[d] = make_float2(0.f, 0.f);
+    load_tile_async(KVs, vb, 0, p.Sk, C, tid);
     for (int vt = 0; vt < n_tiles; ++vt) {
+        float *cur = KVs + (vt & 1) * TILE * D;
+        if (vt + 1 < n_tiles) load_tile_async(KVs + ((vt + 1) & 1) * TILE * D, vb, (vt + 1) * TILE, p.Sk, C, tid);
+        else __pipeline_commit();
+        __pipeline_wait_prior(1);
         __syncthreads();
-        for (int i = tid; i < TILE * 8; i += 128) {
-            const int t = i >> 3, c = i & 7;
-            const int tok = vt * TILE + t;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tok < p.Sk) v = ldg4(vb + (size_t)tok * C + 4 * c);
-            *reinterpret_cast<float4 *>(KVs + t * KV_LD + 4 * c) = v;
-        }
-        __syncthreads();
+        constexpr int TPL = TOK_PER_WARP / HALVES;
 #pragma unroll 2
-        for (int tt = 0; tt < 8; ++tt) {
-            const int t = 32 * warp + 4 * tt;
-            float4 a[4], vv[4];
+        for (int t = 0; t < TPL; ++t) {
+            const int tl = warp * TOK_PER_WARP + half * TPL + t;
+            const float a = Ss[myrow * s_ld + vt * TILE + tl];
+            const float2 aa = make_float2(a, a);
+            const int sw = ((tl >> 2) & 1) << 2;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(Ss + (rg + 4 * i) * s_ld + vt * TILE + t);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) vv[j] = *reinterpret_cast<const float4 *>(KVs + (t + j) * KV_LD + 4 * dq);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                o[i][0] = fmaf(a[i].x, vv[0].x, fmaf(a[i].y, vv[1].x, fmaf(a[i].z, vv[2].x, fmaf(a[i].w, vv[3].x, o[i][0]))));
-                o[i][1] = fmaf(a[i].x, vv[0].y, fmaf(a[i].y, vv[1].y, fmaf(a[i].z, vv[2].y, fmaf(a[i].w, vv[3].y, o[i][1]))));
-                o[i][2] = fmaf(a[i].x, vv[0].z, fmaf(a[i].y, vv[1].z, fmaf(a[i].z, vv[2].z, fmaf(a[i].w, vv[3].z, o[i][2]))));
-                o[i][3] = fmaf(a[i].x, vv[0].w, fmaf(a[i].y, vv[1].w, fmaf(a[i].z, vv[2].w, fmaf(a[i].w, vv[3].w, o[i][3]))));
+            for (int c = 0; c < 8; ++c) {
+                const float4 vv = *reinterpret_cast<const float4 *>(cur + tl * D + 4 * (c ^ sw));
+                o[2 * c + 0] = __ffma2_rn(aa, make_float2(vv.x, vv.y), o[2 * c + 0]);
+                o[2 * c + 1] = __ffma2_rn(aa, make_float2(vv.z, vv.w), o[2 * c + 1]);
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    float *red = KVs;                               // [4][ROWS][D]
+    // cross-warp (and cross-half) reduction through smem, aliased onto the score slab
+    float *red = Ss;                                // [NW * HALVES][ROWS][RED_LD]
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4 *>(red + (warp * ROWS + rg + 4 * i) * D + 4 * dq) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+    for (int d = 0; d < D / 2; ++d) {
+        red[((warp * HALVES + half) * ROWS + myrow) * RED_LD + 2 * d] = o[d].x;
+        red[((warp * HALVES + half) * ROWS + myrow) * RED_LD + 2 * d + 1] = o[d].y;
+    }
     __syncthreads();
     float w0 = 1.f;
     if (p.level_weight) {                           // softmax over the level weights (:264)
@@ -239,44 +265,55 @@ __global__ void __launch_bounds__(128) qtatt_coarse_kernel(CoarseParams p, int s
         for (int l = 0; l < p.levels; ++l) mx = fmaxf(mx, __ldg(p.level_weight + l));
         for (int l = 0; l < p.levels; ++l) den += expf(__ldg(p.level_weight + l) - mx);
         w0 = expf(__ldg(p.level_weight) - mx) / den;
+        if (p.wsm && blockIdx.x == 0 && blockIdx.y == 0 && tid < p.levels)      // the finer levels read their weight from here
+            p.wsm[tid] = expf(__ldg(p.level_weight + tid) - mx) / den;
     }
-    {
-        const int r = tid >> 3, c = tid & 7;        // 16 rows x 8 float4
+    for (int i = tid; i < ROWS * D; i += NW * 32) {
+        const int r = i >> 5, d = i & 31;
         if (row0 + r < p.Sq) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float4 t = *reinterpret_cast<const float4 *>(red + (w * ROWS + r) * D + 4 * c);
-                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-            }
-            s.x *= w0; s.y *= w0; s.z *= w0; s.w *= w0;
-            *reinterpret_cast<float4 *>(p.acc + ((size_t)b * p.Sq + row0 + r) * C + h * D + 4 * c) = s;
+            for (int w = 0; w < NW * HALVES; ++w) s += red[(w * ROWS + r) * RED_LD + d];
+            p.acc[((size_t)b * p.Sq + row0 + r) * C + h * D + d] = (s / rsum[r]) * w0;
         }
     }
 }
 
-}  // namespace
+int coarse_s_ld(int Sk) { return ((Sk + TILE - 1) / TILE * TILE) | 1; }     // odd: conflict-free lane=row access
 
-static int coarse_s_ld(int Sk) { return (Sk + TILE - 1) / TILE * TILE + 4; }
-
-size_t coarse_smem_bytes(int Sk) {
-    return sizeof(float) * ((size_t)ROWS * coarse_s_ld(Sk) + ROWS * Q_LD + TILE * KV_LD + 4 * LIST_CAP) + sizeof(int) * 4 * LIST_CAP;
+size_t smem_bytes(int Sk, int rows) {
+    const size_t slab = (size_t)rows * coarse_s_ld(Sk);
+    const size_t red = (size_t)NW * 32 * RED_LD;                             // aliased onto the slab
+    return sizeof(float) * (2 * TILE * D + (slab > red ? slab : red) + NW * LIST_CAP + 32) + sizeof(int) * NW * LIST_CAP;
 }
 
+}  // namespace
+
+size_t coarse_smem_bytes(int Sk) { return smem_bytes(Sk, 32) <= 227 * 1024 ? smem_bytes(Sk, 32) : smem_bytes(Sk, 16); }
+
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
-    const size_t smem = coarse_smem_bytes(p.Sk);
+    // 32-row CTAs are the efficient shape (all lanes own a row); with too few of them to give every SM two, 16-row CTAs
+    // (lane halves split the tokens) spread the same work over twice as many CTAs
+    const long long ctas32 = (long long)((p.Sq + 31) / 32) * p.B * p.nh;
+    const bool rows32 = smem_bytes(p.Sk, 32) <= 227 * 1024 && ctas32 >= 2 * 148;
+    const size_t smem = rows32 ? smem_bytes(p.Sk, 32) : smem_bytes(p.Sk, 16);
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED,
                    "coarsest level has %d keys; the dense level supports at most ~3300 (shared memory)", p.Sk);
     CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= p.Sk, CASMTR_E_INVALID, "coarse top-k %d must be in [1, min(32, %d)]", p.topk, p.Sk);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(qtatt_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
         attr_set = true;
     }
-    dim3 grid((p.Sq + ROWS - 1) / ROWS, p.B * p.nh);
+    const int rows = rows32 ? 32 : 16;
+    dim3 grid((p.Sq + rows - 1) / rows, p.B * p.nh);
     LaunchScope ls(CASMTR_K_QT_COARSE, stream);
-    qtatt_coarse_kernel<<<grid, 128, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    if (rows32) qtatt_coarse_kernel<32><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    else qtatt_coarse_kernel<16><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
     CASMTR_CHECK_LAUNCH("qtatt_coarse_kernel");
     return CASMTR_OK;
 }

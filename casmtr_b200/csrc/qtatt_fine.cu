@@ -1,7 +1,7 @@
-// Fused quadtree fine level / cascade window attention ("quad attention").
+// Fused quadtree fine level / cascade window attention ("quad attention"), one work item per warp.
 //
 // One warp = one (batch, parent token, head): the 4 sibling queries of the parent attend to the
-// 4*kp candidate keys (the 4 children of each of the parent's kp selected coarser keys).  The
+// KC = 4*kp candidate keys (the 4 children of each of the parent's kp selected coarser keys).  The
 // kernel fuses what the reference does with ~40 torch ops and 2 custom kernels per level:
 // candidate expansion, gathered Q.K^T, softmax, top-k for the next level, gathered A.V, the
 // child-major -> raster reorder and the (weighted) merge with the coarser levels' message.
@@ -11,46 +11,77 @@
 // QTAttA.process_fine_level :46-99, merge :130-138;  CascadeQTAttB.forward :400-452;
 // kernels replaced: src/score_computation_kernal.cu:22-62, src/value_aggregation_kernel.cu:21-42.
 //
-// Data movement: a (token, head) K or V row is one 128-byte line; 8 lanes read one row with
-// LDG.128, so a warp-wide load touches exactly 4 lines (no sector waste).  Every loaded K/V
-// element feeds 4 FMAs (one per sibling query) straight from registers; partial dot products are
-// combined with a transposing butterfly (7 shuffles per 8 candidates), after which each lane
-// owns one (query, candidate) logit per step -- the layout softmax and top-k work in.
-//
-// lane = g*8 + dq:  g in 0..3 (child slot of the candidate being loaded / query row in the
-// epilogue), dq in 0..7 (which float4 of the 32-dim head row).  After the butterfly lane holds
-// logit(query fq = dq&3, parent-candidate 2t + (dq>>2), child g) for step t.
+// Data movement.  The kernel is a gather: every candidate K and V row of a head is one 128-byte line
+// of the token-major feature map, mostly served by L2 (the maps are 11-22 MB).  A warp first issues ALL
+// of its gathers as 16-byte cp.async (LDGSTS) straight into its private shared-memory slab -- 8 lanes
+// per row, 4 rows per instruction, no registers held -- and only then computes:
+//   Q.K^T    lane = candidate (round r: candidate 32r + lane).  K rows are XOR-swizzled in 16-byte chunks
+//            so the per-lane row reads are bank-conflict free; the 4 sibling q rows are broadcast reads,
+//            loaded once per chunk and reused across the rounds.  FMAs are issued as packed FFMA2
+//            (2 fp32 FMAs per instruction, sm_100): the kernel is issue-bound, not bandwidth-bound.
+//   softmax  warp reductions (type B: over all candidates; type A: over the 4 children of a parent
+//            candidate = 4 adjacent lanes, times the parent's score).
+//   top-k    threshold + rank counting, no serial selection: T = k-th largest of the 32 lane maxima,
+//            survivors {a >= T} are compacted (k <= n, typically n < 2k) and ranked against each other
+//            with shuffles; rank < k owns output slot `rank` (descending order, ties: lower candidate).
+//   A.V      lane = (child slot g, 16-byte chunk dq): 3 LDS.128 per 8 FFMA2, then a transposing
+//            butterfly over g leaves query g's output chunk in the lane; merged and stored raster.
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace {
 
 constexpr int D = 32;
-constexpr int WARPS = 8;
 
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
-    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+__device__ __forceinline__ unsigned okey(float v) { return v >= 0.f ? __float_as_uint(v) + 1u : 0u; }   // order preserving, 0 = dead
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// acc.x + acc.y accumulates dot(q, k) over a 4-float chunk with two packed FMAs
+__device__ __forceinline__ float2 dot4p(const float4 q, const float4 k, float2 acc) {
+    acc = __ffma2_rn(make_float2(q.x, q.y), make_float2(k.x, k.y), acc);
+    return __ffma2_rn(make_float2(q.z, q.w), make_float2(k.z, k.w), acc);
 }
 
-template <int T, bool CASCADE, bool TYPE_A, bool DO_TOPK>
-__global__ void __launch_bounds__(WARPS * 32, 2) quad_attention_kernel(FineParams p) {
-    __shared__ __align__(16) float Asm[WARPS][8 * T * 4];
-    __shared__ int stg_idx[DO_TOPK ? WARPS : 1][4 * 32];
-    __shared__ float stg_sc[DO_TOPK ? WARPS : 1][4 * 32];
+template <int R>
+__device__ __forceinline__ float pick(const float (&x)[R][4], int r, int f) {      // x[r][f] with a runtime f, no local memory
+    return f == 0 ? x[r][0] : f == 1 ? x[r][1] : f == 2 ? x[r][2] : x[r][3];
+}
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 3, dq = lane & 7, fq = dq & 3, jj = dq >> 2;
+// floats of shared memory one warp needs for kp parent candidates:
+//   K slab [max(KC,32)][32] (later aliased by A2[KC][8], top-k staging and scratch), V slab [KC][32], Q [4][32]
+__host__ __device__ inline int warp_slab_floats(int kp) {
+    const int kc = 4 * kp;
+    const int krows = kc < 32 ? 32 : kc;
+    return krows * D + kc * D + 4 * D;
+}
+
+// KP > 0: compile-time number of parent candidates (gather loops fully unrolled); KP == 0: runtime p.kp
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+__device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b, int parent, int h, int lane) {
+    const int g = lane >> 3, dq = lane & 7;
     const int wp = p.w0 >> 1;
     const int Np = (p.h0 >> 1) * wp;
-    const long long item = (long long)blockIdx.x * WARPS + warp;
-    if (item >= (long long)p.B * Np * p.nh) return;
-    const int h = (int)(item % p.nh);
-    const int parent = (int)((item / p.nh) % Np);
-    const int b = (int)(item / ((long long)p.nh * Np));
     const int py = parent / wp, px = parent - py * wp;
     const int C = p.nh * D, L0 = p.h0 * p.w0, L1 = p.h1 * p.w1;
-    const int kp = p.kp, KC = 4 * kp;
+    const int kp = KP ? KP : p.kp, KC = 4 * kp;
     const float scale = rsqrtf((float)D);
+
+    // Ks: this warp's slab, [max(KC,32)][32], chunk-swizzled
+    float *Vs = Ks + (KC < 32 ? 32 : KC) * D;                  // [KC][32]
+    float *Qs = Vs + KC * D;                                   // [4][32]
+    // after Q.K^T the K slab and Q are dead and get reused:
+    float *A2 = Ks;                                            // [KC][8]: (a0,a0,a1,a1,a2,a2,a3,a3)
+    float *stg_sc = Ks + 8 * KC;                               // [4][32] top-k scores        (8*KC + 256 <= max(KC,32)*32)
+    unsigned *lkey = (unsigned *)(Ks + 8 * KC + 128);          // [64] survivor keys
+    int *lpos = (int *)(Ks + 8 * KC + 192);                    // [64] survivor candidate positions
+    int *stg_idx = (int *)Qs;                                  // [4][32] top-k token indices
 
     // ---- candidate bases: lane k (< kp) holds the top-left child of parent-candidate k
     int base = 0;
@@ -68,152 +99,259 @@ __global__ void __launch_bounds__(WARPS * 32, 2) quad_attention_kernel(FineParam
         }
     }
     const int off_g = (g >> 1) * p.dil * p.w1 + (g & 1) * p.dil;
-    int qtok[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) qtok[f] = (2 * py + (f >> 1)) * p.w0 + 2 * px + (f & 1);
+    const int qtok0 = 2 * py * p.w0 + 2 * px;      // sibling f of the parent is query token qtok0 + (f>>1)*w0 + (f&1)
+#define QTOK(f) (qtok0 + ((f) >> 1) * p.w0 + ((f) & 1))
 
-    float4 q[4];
+    // ---- issue every gather of this item: Q (1 instruction), K and V rows (2 per parent candidate)
+    {
+        const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
+        const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
+        cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq);
+        // row 4u+g lands at chunk dq ^ ((4u+g) & 7) = dq ^ (4*(u&1) + g)
+        float *kd0 = Ks + g * D + 4 * (dq ^ g), *kd1 = Ks + g * D + 4 * (dq ^ (4 + g));
+        float *vd = Vs + g * D + 4 * dq;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) q[f] = ldg4(p.q + ((size_t)b * L0 + qtok[f]) * C + h * D + 4 * dq);
+        for (int u = 0; u < (KP ? KP : 32); ++u) {
+            if (KP == 0 && u >= kp) break;
+            int tok = __shfl_sync(FULL_MASK, base, u) + off_g;
+            if (CASCADE) tok = min(max(tok, 0), L1 - 1);       // the reference's clamp (:428); QTAtt children are always in range
+            const size_t off = (size_t)tok * C;
+            cp_async16(((u & 1) ? kd1 : kd0) + u * 4 * D, kb + off);
+            cp_async16(vd + u * 4 * D, vb + off);
+        }
+        cp_async_commit();
+    }
 
-    const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
-    const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
-
-    // ---- gathered Q.K^T
-    float sc[T];
+    // ---- gathered Q.K^T, lane = candidate
+    cp_async_wait<0>();
+    __syncwarp();
+    float sc[R][4];
+    {
+        float2 acc[R][4];
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const int ca = min(max(__shfl_sync(FULL_MASK, base, (2 * t) & 31) + off_g, 0), L1 - 1);
-        const int cb = min(max(__shfl_sync(FULL_MASK, base, (2 * t + 1) & 31) + off_g, 0), L1 - 1);
-        float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kbv = ka;
-        if (2 * t < kp) ka = ldg4(kb + (size_t)ca * C);
-        if (2 * t + 1 < kp) kbv = ldg4(kb + (size_t)cb * C);
-        float v[4];
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[r][f] = make_float2(0.f, 0.f);
+        const float *krow[R];                       // rows past KC re-read the last valid row; their scores are masked below
+        int ksw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int c = min(32 * r + lane, KC - 1);
+            krow[r] = Ks + c * D;
+            ksw[r] = c & 7;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 qv[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + f * D + 4 * j);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 kv = *reinterpret_cast<const float4 *>(krow[r] + 4 * (j ^ ksw[r]));
+#pragma unroll
+                for (int f = 0; f < 4; ++f) acc[r][f] = dot4p(qv[f], kv, acc[r][f]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) sc[r][f] = acc[r][f].x + acc[r][f].y;
+    }
+    __syncwarp();                                   // K slab and Q are dead from here on (A2 / staging alias them)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int c = 32 * r + lane;
+        const bool valid = c < KC;
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            const float pa = dot4(q[f], ka), pb = dot4(q[f], kbv);
-            const float recv = __shfl_xor_sync(FULL_MASK, jj ? pa : pb, 4);
-            v[f] = (jj ? pb : pa) + recv;
-        }
-        float w[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float recv = __shfl_xor_sync(FULL_MASK, (dq & 2) ? v[i] : v[i + 2], 2);
-            w[i] = ((dq & 2) ? v[i + 2] : v[i]) + recv;
-        }
-        const float recv = __shfl_xor_sync(FULL_MASK, (dq & 1) ? w[0] : w[1], 1);
-        float s = (((dq & 1) ? w[1] : w[0]) + recv) * scale;
-        const bool valid = 2 * t + jj < kp;
-        if (CASCADE && p.rel_pos != nullptr && valid)
-            s += __ldg(p.rel_pos + (((size_t)b * p.nh + h) * L0 + qtok[fq]) * KC + 4 * (2 * t + jj) + g);
-        sc[t] = valid ? s : -INFINITY;
-    }
-
-    // ---- softmax
-    float a[T];
-    if (!TYPE_A) {      // over all 4*kp candidates of query fq (lanes differing in bits 2,3,4)
-        float m = sc[0];
-#pragma unroll
-        for (int t = 1; t < T; ++t) m = fmaxf(m, sc[t]);
-        m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 16));
-        float sum = 0.f;
-#pragma unroll
-        for (int t = 0; t < T; ++t) { a[t] = exp_neg(sc[t] - m); sum += a[t]; }
-        sum += __shfl_xor_sync(FULL_MASK, sum, 4);
-        sum += __shfl_xor_sync(FULL_MASK, sum, 8);
-        sum += __shfl_xor_sync(FULL_MASK, sum, 16);
-#pragma unroll
-        for (int t = 0; t < T; ++t) a[t] = a[t] / sum;
-    } else {            // QTAttA: over the 4 children of each parent candidate, times the parent's score (:72-77)
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            float m = sc[t];
-            m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 8));
-            m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 16));
-            const bool valid = 2 * t + jj < kp;
-            float e = valid ? exp_neg(sc[t] - m) : 0.f;
-            float sum = e;
-            sum += __shfl_xor_sync(FULL_MASK, sum, 8);
-            sum += __shfl_xor_sync(FULL_MASK, sum, 16);
-            const float ps = __shfl_sync(FULL_MASK, pscore, (2 * t + jj) & 31);
-            a[t] = valid ? (e / sum) * ps : 0.f;
-            sc[t] = valid ? a[t] : -INFINITY;       // type A selects on the redistributed score
+            float s = sc[r][f] * scale;
+            if (CASCADE && p.rel_pos != nullptr && valid)
+                s += __ldg(p.rel_pos + (((size_t)b * p.nh + h) * L0 + QTOK(f)) * KC + c);
+            sc[r][f] = valid ? s : -INFINITY;
         }
     }
 
-    // ---- top-k for the next level: the 4 queries run in parallel in their own lane groups
+    // ---- softmax -> a[r][f]; sc[r][f] becomes the selection score (>= 0, -1 = invalid)
+    float a[R][4];
+    if (!TYPE_A) {      // over all candidates of sibling f
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float m = sc[0][f];
+#pragma unroll
+            for (int r = 1; r < R; ++r) m = fmaxf(m, sc[r][f]);
+            m = warp_max(m);
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { a[r][f] = exp_neg(sc[r][f] - m); sum += a[r][f]; }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                a[r][f] = a[r][f] * inv;
+                sc[r][f] = 32 * r + lane < KC ? a[r][f] : -1.f;
+            }
+        }
+    } else {            // QTAttA: over the 4 children of each parent candidate (4 adjacent lanes), times the parent's score (:72-77)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool valid = 32 * r + lane < KC;
+            const float ps = __shfl_sync(FULL_MASK, pscore, (8 * r + (lane >> 2)) & 31);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                float m = sc[r][f];
+                m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
+                const float e = valid ? exp_neg(sc[r][f] - m) : 0.f;
+                float sum = e;
+                sum += __shfl_xor_sync(FULL_MASK, sum, 1);
+                sum += __shfl_xor_sync(FULL_MASK, sum, 2);
+                a[r][f] = valid ? (e / sum) * ps : 0.f;
+                sc[r][f] = valid ? a[r][f] : -1.f;      // type A selects on the redistributed score
+            }
+        }
+    }
+
+    // ---- top-k for the next level
     if (DO_TOPK) {
-        const unsigned gmask = 0x11111111u << fq;
-        for (int it = 0; it < p.topk; ++it) {
-            float lm = sc[0];
+        const int k = p.topk;
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) {
+            unsigned key[R];
+            unsigned km = 0;
 #pragma unroll
-            for (int t = 1; t < T; ++t) lm = fmaxf(lm, sc[t]);
-            float gm = fmaxf(lm, __shfl_xor_sync(FULL_MASK, lm, 4));
-            gm = fmaxf(gm, __shfl_xor_sync(FULL_MASK, gm, 8));
-            gm = fmaxf(gm, __shfl_xor_sync(FULL_MASK, gm, 16));
-            const unsigned bal = __ballot_sync(FULL_MASK, lm == gm) & gmask;
-            const int owner = __ffs(bal) - 1;
-            int ts = -1;
+            for (int r = 0; r < R; ++r) {
+                key[r] = okey(pick<R>(sc, r, f));
+                km = max(km, key[r]);
+            }
+            // T = k-th largest of the 32 lane maxima; at least k candidates are >= T
+            int above = 0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) above += __shfl_sync(FULL_MASK, km, l) > km;
+            const unsigned T = __reduce_min_sync(FULL_MASK, (above < k && km > 0) ? km : 0xffffffffu);
+            // compact the survivors {key >= T} in candidate order
+            int n = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool pred = key[r] >= T && key[r] > 0;
+                const unsigned bal = __ballot_sync(FULL_MASK, pred);
+                const int pos = n + __popc(bal & ((1u << lane) - 1u));
+                if (pred && pos < 64) { lkey[pos] = key[r]; lpos[pos] = 32 * r + lane; }
+                n += __popc(bal);
+            }
+            __syncwarp();
+            int slot_c = 0;                          // candidate position owning output slot `lane`
+            if (n <= 64) {
+                // rank every survivor among the survivors: descending key, ties by list position (= candidate order)
+                const unsigned ka = lane < n ? lkey[lane] : 0u, kb2 = lane + 32 < n ? lkey[lane + 32] : 0u;
+                const int pa = lane < n ? lpos[lane] : 0, pb = lane + 32 < n ? lpos[lane + 32] : 0;
+                int ra = 0, rb = 0;
+                if (n <= 32) {
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) {
+                        const unsigned oa = __shfl_sync(FULL_MASK, ka, l);
+                        ra += (oa > ka) || (oa == ka && l < lane);
+                    }
+                } else {
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) {
+                        const unsigned oa = __shfl_sync(FULL_MASK, ka, l), ob = __shfl_sync(FULL_MASK, kb2, l);
+                        ra += ((oa > ka) || (oa == ka && l < lane)) + (ob > ka);
+                        rb += (oa >= kb2) + ((ob > kb2) || (ob == kb2 && l < lane));
+                    }
+                }
+                __syncwarp();                        // every lane holds its list entries in registers
+                if (lane < n && ra < k) lpos[ra] = pa;
+                if (lane + 32 < n && rb < k) lpos[rb] = pb;
+                __syncwarp();
+                if (lane < k) slot_c = lpos[lane];
+            } else {
+                // massive ties (> 64 survivors): serial warp arg-max, exact but slow
+                for (int it = 0; it < k; ++it) {
+                    unsigned best = 0;
+                    int br = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (key[r] > best) { best = key[r]; br = r; }
+                    const unsigned gmax = __reduce_max_sync(FULL_MASK, best);
+                    const int owner = __ffs(__ballot_sync(FULL_MASK, best == gmax)) - 1;
+                    const int c = __shfl_sync(FULL_MASK, 32 * br + lane, owner);
+                    if (lane == owner) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (r == br) key[r] = 0;
+                    }
+                    if (lane == it) slot_c = c;
+                }
+            }
+            __syncwarp();
+            // slot -> (token index at this level, score); the owner lane of candidate c holds its score
             float av = 0.f;
 #pragma unroll
-            for (int t = 0; t < T; ++t)
-                if (ts < 0 && sc[t] == gm) { ts = t; av = a[t]; }
-            if (lane == owner) {
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                    if (t == ts) {
-                        sc[t] = -INFINITY;
-                        if (TYPE_A && !p.final_level) a[t] = 0.f;   // selected keys leave the message (:81-84)
-                    }
+            for (int r = 0; r < R; ++r) {
+                const float t = __shfl_sync(FULL_MASK, pick<R>(a, r, f), slot_c & 31);
+                if ((slot_c >> 5) == r) av = t;
             }
-            const int slot = __shfl_sync(FULL_MASK, 4 * (2 * ts + jj) + g, owner & 31);
-            const float aval = __shfl_sync(FULL_MASK, av, owner & 31);
-            const int cf = slot & 3;
-            const int cand = min(max(__shfl_sync(FULL_MASK, base, (slot >> 2) & 31) + (cf >> 1) * p.dil * p.w1 + (cf & 1) * p.dil, 0), L1 - 1);
-            if (lane == fq) { stg_idx[warp][fq * 32 + it] = cand; stg_sc[warp][fq * 32 + it] = aval; }
+            const int cf = slot_c & 3;
+            int cand = __shfl_sync(FULL_MASK, base, (slot_c >> 2) & 31) + (cf >> 1) * p.dil * p.w1 + (cf & 1) * p.dil;
+            if (CASCADE) cand = min(max(cand, 0), L1 - 1);
+            if (lane < k) { stg_idx[f * 32 + lane] = cand; stg_sc[f * 32 + lane] = av; }
+            if (TYPE_A && !p.final_level) {          // selected keys leave the message (:81-84)
+                for (int s = 0; s < k; ++s) {
+                    const int cs = __shfl_sync(FULL_MASK, slot_c, s);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (cs == 32 * r + lane) {
+                            if (f == 0) a[r][0] = 0.f; else if (f == 1) a[r][1] = 0.f; else if (f == 2) a[r][2] = 0.f; else a[r][3] = 0.f;
+                        }
+                }
+            }
         }
         __syncwarp();
-        for (int i = lane; i < 4 * p.topk; i += 32) {
-            const int f = i / p.topk, kk = i - f * p.topk;
-            const size_t o = (((size_t)b * L0 + qtok[f]) * p.nh + h) * p.topk + kk;
-            p.topk_idx[o] = stg_idx[warp][f * 32 + kk];
-            p.topk_score[o] = stg_sc[warp][f * 32 + kk];
+        for (int i = lane; i < 4 * k; i += 32) {
+            const int f = i / k, kk = i - f * k;
+            const size_t o = (((size_t)b * L0 + QTOK(f)) * p.nh + h) * k + kk;
+            p.topk_idx[o] = stg_idx[f * 32 + kk];
+            p.topk_score[o] = stg_sc[f * 32 + kk];
         }
     }
 
-    // ---- A -> smem as [slot][query] so the A.V loop reads the 4 sibling weights with one LDS.128
+    // ---- A -> smem as [candidate][sibling pairs]: the A.V loop reads broadcast pairs for FFMA2
 #pragma unroll
-    for (int t = 0; t < T; ++t) Asm[warp][(4 * (2 * t + jj) + g) * 4 + fq] = a[t];
+    for (int r = 0; r < R; ++r)
+        if (32 * r + lane < KC) {
+            float4 *dst = reinterpret_cast<float4 *>(A2 + (32 * r + lane) * 8);
+            dst[0] = make_float4(a[r][0], a[r][0], a[r][1], a[r][1]);
+            dst[1] = make_float4(a[r][2], a[r][2], a[r][3], a[r][3]);
+        }
     __syncwarp();
 
-    // ---- gathered A.V: lane accumulates all 4 queries x its 4 dims over the candidates of child slot g
-    float o[4][4];
+    // ---- gathered A.V: lane accumulates all 4 siblings x its 4 dims over the candidates of child slot g
+    float2 o[4][2];
 #pragma unroll
-    for (int f = 0; f < 4; ++f)
+    for (int f = 0; f < 4; ++f) o[f][0] = o[f][1] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) o[f][c] = 0.f;
-#pragma unroll
-    for (int u = 0; u < 2 * T; ++u) {
-        const int cand = min(max(__shfl_sync(FULL_MASK, base, u & 31) + off_g, 0), L1 - 1);
-        if (u < kp) {
-            const float4 vv = ldg4(vb + (size_t)cand * C);
-            const float4 aw = *reinterpret_cast<const float4 *>(&Asm[warp][(4 * u + g) * 4]);
-            o[0][0] = fmaf(aw.x, vv.x, o[0][0]); o[0][1] = fmaf(aw.x, vv.y, o[0][1]); o[0][2] = fmaf(aw.x, vv.z, o[0][2]); o[0][3] = fmaf(aw.x, vv.w, o[0][3]);
-            o[1][0] = fmaf(aw.y, vv.x, o[1][0]); o[1][1] = fmaf(aw.y, vv.y, o[1][1]); o[1][2] = fmaf(aw.y, vv.z, o[1][2]); o[1][3] = fmaf(aw.y, vv.w, o[1][3]);
-            o[2][0] = fmaf(aw.z, vv.x, o[2][0]); o[2][1] = fmaf(aw.z, vv.y, o[2][1]); o[2][2] = fmaf(aw.z, vv.z, o[2][2]); o[2][3] = fmaf(aw.z, vv.w, o[2][3]);
-            o[3][0] = fmaf(aw.w, vv.x, o[3][0]); o[3][1] = fmaf(aw.w, vv.y, o[3][1]); o[3][2] = fmaf(aw.w, vv.z, o[3][2]); o[3][3] = fmaf(aw.w, vv.w, o[3][3]);
-        }
+    for (int u = 0; u < (KP ? KP : 32); ++u) {
+        if (KP == 0 && u >= kp) break;
+        const float4 vv = *reinterpret_cast<const float4 *>(Vs + (4 * u + g) * D + 4 * dq);
+        const float4 a01 = *reinterpret_cast<const float4 *>(A2 + (4 * u + g) * 8);
+        const float4 a23 = *reinterpret_cast<const float4 *>(A2 + (4 * u + g) * 8 + 4);
+        const float2 vlo = make_float2(vv.x, vv.y), vhi = make_float2(vv.z, vv.w);
+        o[0][0] = __ffma2_rn(make_float2(a01.x, a01.y), vlo, o[0][0]); o[0][1] = __ffma2_rn(make_float2(a01.x, a01.y), vhi, o[0][1]);
+        o[1][0] = __ffma2_rn(make_float2(a01.z, a01.w), vlo, o[1][0]); o[1][1] = __ffma2_rn(make_float2(a01.z, a01.w), vhi, o[1][1]);
+        o[2][0] = __ffma2_rn(make_float2(a23.x, a23.y), vlo, o[2][0]); o[2][1] = __ffma2_rn(make_float2(a23.x, a23.y), vhi, o[2][1]);
+        o[3][0] = __ffma2_rn(make_float2(a23.z, a23.w), vlo, o[3][0]); o[3][1] = __ffma2_rn(make_float2(a23.z, a23.w), vhi, o[3][1]);
     }
-    // reduce over g (lane bits 3,4), transposing: lane ends with query f = g
+    // reduce over g (lane bits 3,4), transposing: lane ends with sibling f = g
+    float ov[4][4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { ov[f][0] = o[f][0].x; ov[f][1] = o[f][0].y; ov[f][2] = o[f][1].x; ov[f][3] = o[f][1].y; }
     float r2[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float recv = __shfl_xor_sync(FULL_MASK, (g & 2) ? o[i][c] : o[i + 2][c], 16);
-            r2[i][c] = ((g & 2) ? o[i + 2][c] : o[i][c]) + recv;
+            const float recv = __shfl_xor_sync(FULL_MASK, (g & 2) ? ov[i][c] : ov[i + 2][c], 16);
+            r2[i][c] = ((g & 2) ? ov[i + 2][c] : ov[i][c]) + recv;
         }
     float m4[4];
 #pragma unroll
@@ -223,19 +361,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) quad_attention_kernel(FineParam
     }
 
     // ---- merge with the coarser levels and write raster (:262-284)
-    float wl = 1.f;
-    if (p.level_weight) {
-        float mx = -INFINITY, den = 0.f;
-        for (int l = 0; l < p.levels; ++l) mx = fmaxf(mx, __ldg(p.level_weight + l));
-        for (int l = 0; l < p.levels; ++l) den += expf(__ldg(p.level_weight + l) - mx);
-        wl = expf(__ldg(p.level_weight + p.level) - mx) / den;
-    }
+    const float wl = p.wsm ? __ldg(p.wsm + p.level) : 1.f;      // softmax(weight)[level], normalised once by the coarse kernel
     float4 res = make_float4(m4[0] * wl, m4[1] * wl, m4[2] * wl, m4[3] * wl);
     if (p.acc_prev) {
         const float4 ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
         res.x = ap.x + res.x; res.y = ap.y + res.y; res.z = ap.z + res.z; res.w = ap.w + res.w;
     }
-    *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + qtok[g]) * C + h * D + 4 * dq) = res;
+    *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq) = res;
 
     // ---- cascade: the window's key indices for the 4 children (the reference's upsampled_idx, :450)
     if (CASCADE && p.upsampled_idx != nullptr && h == 0) {
@@ -245,30 +377,91 @@ __global__ void __launch_bounds__(WARPS * 32, 2) quad_attention_kernel(FineParam
             const int cand = min(max(__shfl_sync(FULL_MASK, base, (s >> 2) & 31) + (cf >> 1) * p.dil * p.w1 + (cf & 1) * p.dil, 0), L1 - 1);
             if (s < KC) {
 #pragma unroll
-                for (int f = 0; f < 4; ++f) p.upsampled_idx[((size_t)b * L0 + qtok[f]) * KC + s] = cand;
+                for (int f = 0; f < 4; ++f) p.upsampled_idx[((size_t)b * L0 + QTOK(f)) * KC + s] = cand;
             }
         }
     }
+#undef QTOK
 }
 
-template <int T, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+// grid.x covers the (parent, head) items of one batch element, grid.y = batch
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+__global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int warps_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Np = (p.h0 >> 1) * (p.w0 >> 1);
+    const unsigned item = blockIdx.x * (unsigned)warps_per_cta + warp;
+    if (item >= (unsigned)(Np * p.nh)) return;
+    const int parent = item / (unsigned)p.nh, h = item - parent * p.nh;
+    quad_item<KP, R, CASCADE, TYPE_A, DO_TOPK>(p, smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp), blockIdx.y, parent, h, lane);
+}
+
+// persistent variant over a device-side list of cells (b * Np + parent), all heads of each: the cascade fallback
+template <int KP, int R>
+__global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, int warps_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Np = (p.h0 >> 1) * (p.w0 >> 1);
+    const int n = *p.item_count * p.nh;
+    float *slab = smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp);
+    for (int i = blockIdx.x * warps_per_cta + warp; i < n; i += gridDim.x * warps_per_cta) {
+        const int cell = p.item_list[i / p.nh], h = i % p.nh;
+        quad_item<KP, R, true, false, false>(p, slab, cell / Np, cell % Np, h, lane);
+        __syncwarp();
+    }
+}
+
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
 int launch_t(const FineParams &p, cudaStream_t stream) {
-    const long long items = (long long)p.B * (p.h0 / 2) * (p.w0 / 2) * p.nh;
-    const long long blocks = (items + WARPS - 1) / WARPS;
-    CASMTR_REQUIRE(blocks <= 0x7fffffffLL, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
-    if (blocks == 0) return CASMTR_OK;
+    const long long items = (long long)(p.h0 / 2) * (p.w0 / 2) * p.nh;       // per batch element
+    if (items == 0 || p.B == 0) return CASMTR_OK;
+    // warps per CTA: as many as fit in half an SM's shared memory (two CTAs co-reside), at most 8
+    const size_t per_warp = sizeof(float) * warp_slab_floats(p.kp);
+    int wpc = (int)((113 * 1024) / per_warp);
+    wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+    const size_t smem = per_warp * wpc;
+    const long long blocks = (items + wpc - 1) / wpc;
+    CASMTR_REQUIRE(blocks <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
+    auto kern = quad_attention_kernel<KP, R, CASCADE, TYPE_A, DO_TOPK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        attr_set = true;
+    }
     LaunchScope ls(CASCADE ? CASMTR_K_CASCADE_ATT : (DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST), stream);
-    quad_attention_kernel<T, CASCADE, TYPE_A, DO_TOPK><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(p);
+    kern<<<dim3((unsigned)blocks, p.B), wpc * 32, smem, stream>>>(p, wpc);
     CASMTR_CHECK_LAUNCH("quad_attention_kernel");
     return CASMTR_OK;
 }
 
-template <int T>
+template <int KP, int R>
+int launch_list_t(const FineParams &p, cudaStream_t stream) {
+    const size_t per_warp = sizeof(float) * warp_slab_floats(p.kp);
+    int wpc = (int)((113 * 1024) / per_warp);
+    wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+    const size_t smem = per_warp * wpc;
+    auto kern = quad_attention_list_kernel<KP, R>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        attr_set = true;
+    }
+    LaunchScope ls(CASMTR_K_CASCADE_FALLBACK, stream);
+    kern<<<2 * 148, wpc * 32, smem, stream>>>(p, wpc);             // persistent: the list length is only known on the device
+    CASMTR_CHECK_LAUNCH("quad_attention_list_kernel");
+    return CASMTR_OK;
+}
+
+template <int KP, int R>
 int launch_by_flags(const FineParams &p, cudaStream_t stream) {
-    if (p.topk_pos) return launch_t<T, true, false, false>(p, stream);
+    if (p.topk_pos) return launch_t<KP, R, true, false, false>(p, stream);
     const bool topk = p.topk_idx != nullptr;
-    if (p.type_a) return topk ? launch_t<T, false, true, true>(p, stream) : launch_t<T, false, true, false>(p, stream);
-    return topk ? launch_t<T, false, false, true>(p, stream) : launch_t<T, false, false, false>(p, stream);
+    if (p.type_a) return topk ? launch_t<KP, R, false, true, true>(p, stream) : launch_t<KP, R, false, true, false>(p, stream);
+    return topk ? launch_t<KP, R, false, false, true>(p, stream) : launch_t<KP, R, false, false, false>(p, stream);
 }
 
 }  // namespace
@@ -276,9 +469,17 @@ int launch_by_flags(const FineParams &p, cudaStream_t stream) {
 int launch_quad_attention(const FineParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE(p.kp >= 1 && p.kp <= 32, CASMTR_E_UNSUPPORTED, "parent candidate count %d must be in [1,32]", p.kp);
     CASMTR_REQUIRE((p.h0 % 2) == 0 && (p.w0 % 2) == 0, CASMTR_E_INVALID, "query grid %dx%d must be even", p.h0, p.w0);
+    if (p.item_list) {                               // cascade fallback cells of the tile kernel
+        CASMTR_REQUIRE(p.topk_pos && p.kp == 25, CASMTR_E_INVALID, "item lists are a cascade (k = 25) feature");
+        return launch_list_t<25, 4>(p, stream);
+    }
     if (p.topk_idx) CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= 4 * p.kp, CASMTR_E_INVALID, "top-k %d must be in [1, min(32, %d)]", p.topk, 4 * p.kp);
-    if (p.kp <= 8) return launch_by_flags<4>(p, stream);
-    if (p.kp <= 16) return launch_by_flags<8>(p, stream);
-    if (p.kp <= 26) return launch_by_flags<13>(p, stream);
-    return launch_by_flags<16>(p, stream);
+    // the shipped configurations get fully unrolled gather loops; everything else runs the runtime-kp variant
+    if (p.kp == 32) return launch_by_flags<32, 4>(p, stream);
+    if (p.kp == 16) return launch_by_flags<16, 2>(p, stream);
+    if (p.kp == 25) return launch_by_flags<25, 4>(p, stream);
+    if (p.kp <= 8) return launch_by_flags<0, 1>(p, stream);
+    if (p.kp <= 16) return launch_by_flags<0, 2>(p, stream);
+    if (p.kp <= 24) return launch_by_flags<0, 3>(p, stream);
+    return launch_by_flags<0, 4>(p, stream);
 }

@@ -186,10 +186,11 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
 
 # ------------------------------------------------------------------------------------- cascade matching
 def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, temperature=1.0, need_conf=True,
-                          need_conf10=None):
+                          need_conf10=None, w0=0, w1=0):
     """Fused sparse correlation + softmax + argmax, both directions.  Returns dict with conf01/conf10
     (None unless need_conf / need_conf10; need_conf10 defaults to need_conf), next_conf01/10 [B,L] fp32,
-    next_idx01/10 [B,L] int64."""
+    next_idx01/10 [B,L] int64.  w0 / w1: token-grid row lengths (0 = unknown); they only select the faster
+    sibling-sharing kernel, results are identical."""
     if need_conf10 is None:
         need_conf10 = need_conf
     _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
@@ -213,7 +214,7 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
         check(lib().casmtr_cascade_match_fwd(_ptr(feat0), _ptr(feat1), _ptr(idx01), _ptr(idx10), _ptr(m0), _ptr(m1),
                                              float(temperature), _ptr(o['conf01']), _ptr(o['next_conf01']), _ptr(o['next_idx01']),
                                              _ptr(o['conf10']), _ptr(o['next_conf10']), _ptr(o['next_idx10']),
-                                             B, L0, L1, Cc, K, _stream(feat0)), 'casmtr_cascade_match_fwd')
+                                             B, L0, L1, Cc, K, int(w0), int(w1), _stream(feat0)), 'casmtr_cascade_match_fwd')
     return o
 
 

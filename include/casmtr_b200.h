@@ -70,12 +70,13 @@ enum {
     CASMTR_K_QT_COARSE = 1,     /* dense coarsest quadtree level */
     CASMTR_K_QT_FINE_MID = 2,   /* intermediate quadtree levels (emit top-k) */
     CASMTR_K_QT_FINE_LAST = 3,  /* finest quadtree level (merged message only) */
-    CASMTR_K_CASCADE_ATT = 4,   /* CascadeQTAttB window attention */
+    CASMTR_K_CASCADE_ATT = 4,   /* CascadeQTAttB window attention (TMA-tiled, or the gather kernel when not tileable) */
     CASMTR_K_CASCADE_MATCH = 5, /* fused correlation + softmax + argmax */
     CASMTR_K_EXTRACT = 6,       /* NMS / gates / scan / ordered emit */
     CASMTR_K_FINE_MATCH = 7,
     CASMTR_K_OPS = 8,           /* op-level drop-ins (score5d / value_agg / score3d) */
-    CASMTR_K_COUNT = 9
+    CASMTR_K_CASCADE_FALLBACK = 9, /* gather kernel over the cells the TMA-tiled cascade kernels could not serve */
+    CASMTR_K_COUNT = 10
 };
 /* Total number of kernels this library has launched in this process (all threads). */
 CASMTR_API uint64_t casmtr_launch_count(void);
@@ -159,13 +160,17 @@ CASMTR_API int casmtr_cascade_qtatt_fwd(const float *query, const float *key, co
 /* feat0 [B,L0,C], feat1 [B,L1,C] (un-normalised; the 1/sqrt(C) of reference :88 is applied inside);
  * idx01 [B,L0,K], idx10 [B,L1,K] int64; mask0 [B,L0] / mask1 [B,L1] uint8 (both or neither NULL);
  * conf01 / conf10: NULL or [B,L,K] softmax over the K candidates; next_conf* [B,L] fp32 (row max);
- * next_idx* [B,L] int64 = idx[b,i,argmax].  K <= 128, C % 4 == 0. */
+ * next_idx* [B,L] int64 = idx[b,i,argmax].  K <= 128, C % 4 == 0.
+ * w0 / w1: row length of the image-0 / image-1 token grids, or 0 if unknown.  With even grids the kernel
+ * processes the 2x2 sibling tokens of a parent cell together and, when their candidate lists are identical
+ * (they are when idx comes from CascadeQTAttB's upsampled_idx), reads every candidate row once for all four;
+ * results do not depend on w0 / w1. */
 CASMTR_API int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
                              const int64_t *idx01, const int64_t *idx10,
                              const uint8_t *mask0, const uint8_t *mask1, float temperature,
                              float *conf01, float *next_conf01, int64_t *next_idx01,
                              float *conf10, float *next_conf10, int64_t *next_idx10,
-                             int B, int L0, int L1, int C, int K, casmtr_stream_t stream);
+                             int B, int L0, int L1, int C, int K, int w0, int w1, casmtr_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS + match extraction (R7) */
 

@@ -1,0 +1,57 @@
+"""Parity comparators shared by tests/ and __graft_entry__.smoke().  Test infrastructure only -- see oracle/__init__.py."""
+import torch
+
+
+def topk_bad_rows(idx, score, ref_idx, ref_score, what='', rel_gap=1e-5, skip=None):
+    """Top-k parity with a tie guard.  idx/ref_idx [B,L,k,nh] int64, score/ref_score the matching fp32 scores.
+    Returns bad [B,L,nh]: rows whose selected key SETS differ.  A row may differ only by swapping candidates whose
+    scores equal the k-th score to within `rel_gap` (relative): the reference takes torch.topk of fp32 values whose
+    last bits depend on the summation order, and documents no tie rule.  Anything else fails the assertion.
+    Rows flagged in `skip` (descendants of earlier tie rows: their candidate sets legitimately differ) are ignored."""
+    a, ia = torch.sort(idx, dim=2)
+    b, ib = torch.sort(ref_idx, dim=2)
+    bad = (a != b).any(dim=2)                                   # [B,L,nh]
+    if skip is not None:
+        bad = bad & ~skip
+    if not bad.any():
+        return bad
+    sa, sb = torch.gather(score, 2, ia), torch.gather(ref_score, 2, ib)
+    for bi, li, hi in bad.nonzero().tolist():
+        ours = dict(zip(a[bi, li, :, hi].tolist(), sa[bi, li, :, hi].tolist()))
+        ref = dict(zip(b[bi, li, :, hi].tolist(), sb[bi, li, :, hi].tolist()))
+        only_ours = [v for k_, v in ours.items() if k_ not in ref]
+        only_ref = [v for k_, v in ref.items() if k_ not in ours]
+        assert len(only_ours) == len(only_ref), what
+        kth = min(ref.values())
+        for v in only_ours + only_ref:
+            assert abs(v - kth) <= rel_gap * abs(kth) + 1e-12, \
+                f'{what}: row (b={bi}, l={li}, h={hi}) swaps a candidate with score {v} against the k-th score {kth} -- not a tie'
+    return bad
+
+
+def children_rows(mask, h, w):
+    """[B, h*w, nh] bool over a raster grid -> [B, (2h)*(2w), nh]: every cell's flag copied to its 2x2 children."""
+    B, _, nh = mask.shape
+    m = mask.reshape(B, h, 1, w, 1, nh).expand(B, h, 2, w, 2, nh)
+    return m.reshape(B, 4 * h * w, nh)
+
+
+def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3):
+    """Level by level: identical top-k key sets (fp32 near-ties at the k-th place excepted, see topk_bad_rows),
+    scores within 1e-5, and the merged message within `tol` on every (token, head) that does not descend from a tie row.
+    Returns (max message error on clean rows, fraction of tie-tainted rows)."""
+    taint = None                                        # [B, L_i, nh] rows whose candidate sets legitimately differ
+    for i, ti in enumerate(tk_idx):
+        gh, gw = h >> (lv - 1 - i), w >> (lv - 1 - i)
+        bad = topk_bad_rows(ti.cpu(), tk_sc[i].cpu(), aux['topk_idx'][i], aux['topk_score'][i], f'{what} level {i}', skip=taint)
+        taint = bad if taint is None else (taint | bad)
+        d = (torch.sort(tk_sc[i].cpu(), dim=2)[0] - torch.sort(aux['topk_score'][i], dim=2)[0]).abs().amax(dim=2)
+        assert d[~taint].max() < 1e-5, f'{what} level {i}: top-k scores differ'
+        if i < lv - 1:
+            taint = children_rows(taint, gh, gw)
+    frac = taint.float().mean().item()
+    assert frac < 0.05, f'{what}: too many tie rows ({frac:.3f})'
+    diff = (out.cpu() - ref).abs().amax(dim=-1)          # [B, L, nh]
+    err = diff[~taint].max().item()
+    assert err < tol, f'{what}: message differs from the oracle by {err}'
+    return err, frac

@@ -23,3 +23,6 @@ def dev():
 def topk_sets_equal(a, b, k_dim=2):
     """Compare top-k index tensors as sets along k_dim (torch.topk tie/sort order is unspecified)."""
     return torch.equal(torch.sort(a, dim=k_dim)[0], torch.sort(b, dim=k_dim)[0])
+
+
+from oracle.compare import children_rows, topk_bad_rows  # noqa: E402,F401

@@ -22,14 +22,23 @@ def _stage(B, C, h, w, seed, pad=False):
     return d
 
 
+@pytest.mark.parametrize('grid', [False, True, 'mixed'])
 @pytest.mark.parametrize('B,C,h,w,pad', [(2, 128, 32, 32, False), (1, 64, 32, 48, False), (2, 128, 32, 32, True), (1, 256, 16, 16, False)])
-def test_cascade_match(dev, B, C, h, w, pad):
+def test_cascade_match(dev, B, C, h, w, pad, grid):
+    """grid=False: one warp per query row; True: the sibling-sharing kernel (2x2 queries of a parent cell share their
+    candidate rows); 'mixed': some cells get different lists per sibling, which the kernel must detect and handle."""
     d = _stage(B, C, h, w, 31, pad)
+    if grid == 'mixed':
+        g = torch.Generator().manual_seed(77)
+        hit = torch.rand(B, h * w, generator=g) < 0.3
+        d['idx01'][hit] = torch.randint(0, h * w, (int(hit.sum()), 100), generator=g)
+        d['idx10'][:, 5] = torch.randint(0, h * w, (B, 100), generator=g)
     m0 = d['mask0'].flatten(1) if pad else None
     m1 = d['mask1'].flatten(1) if pad else None
     ref = cascade.cascade_match(d['f0'], d['f1'], d['idx01'], d['idx10'], m0, m1, 1.0)
     out = F.cascade_match_forward(d['f0'].to(dev), d['f1'].to(dev), d['idx01'].to(dev), d['idx10'].to(dev),
-                                  None if m0 is None else m0.to(dev), None if m1 is None else m1.to(dev), 1.0)
+                                  None if m0 is None else m0.to(dev), None if m1 is None else m1.to(dev), 1.0,
+                                  w0=w if grid else 0, w1=w if grid else 0)
     for t in ('01', '10'):
         assert torch.equal(out['next_idx' + t].cpu(), ref['next_idx' + t])
         assert (out['next_conf' + t].cpu() - ref['next_conf' + t]).abs().max() < 1e-5

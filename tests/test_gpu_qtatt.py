@@ -9,7 +9,7 @@ from casmtr_b200 import functional as F
 from casmtr_b200 import synth
 from oracle import qtatt
 
-from conftest import topk_sets_equal
+from oracle.compare import check_qtatt_levels
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -17,6 +17,10 @@ TOL = 1e-3
 
 def _cuda(lst, dev):
     return [t.to(dev) for t in lst]
+
+
+def _check_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what):
+    check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=TOL)
 
 
 @pytest.mark.parametrize('B,nh,h,w,topks', [
@@ -33,10 +37,7 @@ def test_qtatt_b(dev, B, nh, h, w, topks):
     ref, aux = qtatt.qtatt_b(qs, ks, vs, wt, topks, nh, return_aux=True)
     out, tk_idx, tk_sc = F.qtatt_forward(_cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev), topks, nh,
                                          weight=wt.to(dev), attn_type='B', return_topk=True)
-    for i, ti in enumerate(tk_idx):
-        assert topk_sets_equal(ti.cpu(), aux['topk_idx'][i]), f'top-k index set mismatch at level {i}'
-        assert (torch.sort(tk_sc[i].cpu(), dim=2)[0] - torch.sort(aux['topk_score'][i], dim=2)[0]).abs().max() < 1e-5
-    assert (out.cpu() - ref).abs().max() < TOL
+    _check_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, 'QTAttB')
 
 
 @pytest.mark.parametrize('B,nh,h,w,topks', [(1, 8, 32, 32, [32, 16, 8]), (2, 4, 16, 24, [8, 8, 4]), (1, 8, 16, 16, [8, 8])])
@@ -46,9 +47,7 @@ def test_qtatt_a(dev, B, nh, h, w, topks):
     ref, aux = qtatt.qtatt_a(qs, ks, vs, topks, nh, return_aux=True)
     out, tk_idx, tk_sc = F.qtatt_forward(_cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev), topks, nh,
                                          attn_type='A', return_topk=True)
-    for i, ti in enumerate(tk_idx):
-        assert topk_sets_equal(ti.cpu(), aux['topk_idx'][i]), f'top-k index set mismatch at level {i}'
-    assert (out.cpu() - ref).abs().max() < TOL
+    _check_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, 'QTAttA')
 
 
 def test_qtatt_b_module_state_dict(dev):
