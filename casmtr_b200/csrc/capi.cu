@@ -292,7 +292,7 @@ int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *
     fp.out = message; fp.upsampled_idx = upsampled_idx;
     fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1;
     fp.kp = k; fp.dil = dilated;
-    if (k == 25 && dilated == 1) {
+    if (k == 25 && dilated == 1 && ((uintptr_t)topk_pos & 15) == 0) {
         // regular 5x5 windows: TMA-tiled kernel for the coherent cells, gather kernel for the listed outliers
         int *fb_count = fb + (size_t)B * (h0 / 2) * (w0 / 2);
         rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, rel_pos, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
@@ -303,12 +303,20 @@ int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *
 }
 
 // ------------------------------------------------------------------------------------------------ cascade matching
+size_t casmtr_cascade_match_workspace_bytes(int B, int L0, int L1) {
+    if (B <= 0 || L0 <= 0 || L1 <= 0) return 0;
+    Workspace ws(nullptr, 0);
+    ws.take<int>((size_t)B * (L0 / 4 + L1 / 4) + 2);
+    return ws.off;
+}
+
 int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
                              const int64_t *idx01, const int64_t *idx10,
                              const uint8_t *mask0, const uint8_t *mask1, float temperature,
                              float *conf01, float *next_conf01, int64_t *next_idx01,
                              float *conf10, float *next_conf10, int64_t *next_idx10,
-                             int B, int L0, int L1, int C, int K, int w0, int w1, casmtr_stream_t stream) {
+                             int B, int L0, int L1, int C, int K, int w0, int w1,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
     CASMTR_REQUIRE(w0 >= 0 && w1 >= 0 && (w0 == 0 || L0 % w0 == 0) && (w1 == 0 || L1 % w1 == 0), CASMTR_E_INVALID,
                    "cascade_match: grid widths %d / %d do not divide L0=%d / L1=%d", w0, w1, L0, L1);
     CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0 && K > 0, CASMTR_E_INVALID, "cascade_match: bad sizes");
@@ -322,6 +330,11 @@ int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
     p.conf01 = conf01; p.conf10 = conf10; p.next_conf01 = next_conf01; p.next_conf10 = next_conf10;
     p.next_idx01 = next_idx01; p.next_idx10 = next_idx10;
     p.B = B; p.L0 = L0; p.L1 = L1; p.C = C; p.K = K; p.w0 = w0; p.w1 = w1;
+    p.fb_list = p.fb_count = nullptr; p.cell_list = p.cell_count = nullptr;
+    if (workspace != nullptr && workspace_bytes >= casmtr_cascade_match_workspace_bytes(B, L0, L1)) {
+        p.fb_list = (int *)workspace;
+        p.fb_count = p.fb_list + (size_t)B * (L0 / 4 + L1 / 4) + 1;
+    }
     return launch_cascade_match(p, (cudaStream_t)stream);
 }
 

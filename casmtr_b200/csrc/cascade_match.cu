@@ -173,16 +173,33 @@ __device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
 
 __host__ __device__ inline int cell_slab_floats(int K, int C) { return (K + 4) * C; }
 
+template <int CH>
+__device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, size_t cell, int lane);
+
 // CH = 16-byte chunks per feature row (C / 4): 32 or 16.  lane = candidate in the compute phase.
 template <int CH>
 __global__ void __launch_bounds__(256) cascade_match_cell_kernel(MatchParams p, int warps_per_cta) {
     extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *slab = smem + (size_t)warp * cell_slab_floats(p.K, 4 * CH);
+    if (p.cell_list) {                            // persistent over the tile kernel's fallback list
+        const int n = *p.cell_count;
+        for (int i = blockIdx.x * warps_per_cta + warp; i < n; i += gridDim.x * warps_per_cta) {
+            match_cell<CH>(p, slab, (size_t)p.cell_list[i], lane);
+            __syncwarp();
+        }
+        return;
+    }
+    const size_t cell = blockIdx.x * (size_t)warps_per_cta + warp;
+    if (cell >= (size_t)p.B * (p.L0 >> 2) + (size_t)p.B * (p.L1 >> 2)) return;
+    match_cell<CH>(p, slab, cell, lane);
+}
+
+template <int CH>
+__device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, size_t cell, int lane) {
     constexpr int C = 4 * CH, RPI = 32 / CH;      // rows per cp.async instruction
     constexpr int R = MAX_CHUNKS / 4;             // candidate rounds of 32
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    size_t cell = blockIdx.x * (size_t)warps_per_cta + warp;
-    const size_t cells0 = (size_t)p.B * (p.L0 >> 2), cells1 = (size_t)p.B * (p.L1 >> 2);
-    if (cell >= cells0 + cells1) return;
+    const size_t cells0 = (size_t)p.B * (p.L0 >> 2);
     const bool rev = cell >= cells0;
     if (rev) cell -= cells0;
     const Dir d = direction(p, rev);
@@ -216,7 +233,7 @@ __global__ void __launch_bounds__(256) cascade_match_cell_kernel(MatchParams p, 
         return;
     }
 
-    float *Ks = smem + (size_t)warp * cell_slab_floats(K, C);   // [K][C], 16-byte chunks XOR-swizzled by (row & 7)
+    float *Ks = slab;                                            // [K][C], 16-byte chunks XOR-swizzled by (row & 7)
     float *Qs = Ks + (size_t)K * C;                              // [4][C]
     const float *kb = d.kf + b * (size_t)d.Lk * C;
     {   // stage the 4 query rows and the K candidate rows (every global read is a full coalesced row)
@@ -324,13 +341,22 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
     if (rows == 0) return CASMTR_OK;
     const bool quad = p.w0 > 0 && p.w1 > 0 && p.w0 % 2 == 0 && p.w1 % 2 == 0 && p.L0 % p.w0 == 0 && p.L1 % p.w1 == 0 &&
                       (p.L0 / p.w0) % 2 == 0 && (p.L1 / p.w1) % 2 == 0 && (p.C == 128 || p.C == 64);
-    LaunchScope ls(CASMTR_K_CASCADE_MATCH, stream);
+    MatchParams q = p;
+    q.cell_list = nullptr; q.cell_count = nullptr;
+    bool listed = false;
+    if (quad && match_tile_applicable(p)) {       // window-structured lists: TMA-tiled kernel, cell kernel over its fallback list
+        const int rc = launch_cascade_match_tile(p, stream);
+        if (rc != CASMTR_OK) return rc;
+        q.cell_list = p.fb_list; q.cell_count = p.fb_count;
+        listed = true;
+    }
+    LaunchScope ls(listed ? CASMTR_K_CASCADE_FALLBACK : CASMTR_K_CASCADE_MATCH, stream);
     if (quad) {
         const size_t per_warp = sizeof(float) * cell_slab_floats(p.K, p.C);
         int wpc = (int)((113 * 1024) / per_warp);
         wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
         const size_t smem = per_warp * wpc;
-        const unsigned blocks = (unsigned)((rows / 4 + wpc - 1) / wpc);
+        const unsigned blocks = listed ? 2 * 148 : (unsigned)((rows / 4 + wpc - 1) / wpc);
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(cascade_match_cell_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -340,8 +366,8 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
             if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
             attr_set = true;
         }
-        if (p.C == 128) cascade_match_cell_kernel<32><<<blocks, wpc * 32, smem, stream>>>(p, wpc);
-        else cascade_match_cell_kernel<16><<<blocks, wpc * 32, smem, stream>>>(p, wpc);
+        if (p.C == 128) cascade_match_cell_kernel<32><<<blocks, wpc * 32, smem, stream>>>(q, wpc);
+        else cascade_match_cell_kernel<16><<<blocks, wpc * 32, smem, stream>>>(q, wpc);
     } else {
         const unsigned blocks = (unsigned)((rows + 7) / 8);
         if (p.C <= 128) cascade_match_row_kernel<1><<<blocks, 256, 0, stream>>>(p);

@@ -81,8 +81,16 @@ struct MatchParams {
     int64_t *next_idx01, *next_idx10;
     int B, L0, L1, C, K;
     int w0, w1;                 // grid widths of image 0 / 1 (0 = unknown: one warp per query row)
+    int *fb_list, *fb_count;    // workspace of the TMA-tiled kernel: cells it could not serve (NULL = tile path off)
+    const int *cell_list;       // cell kernel: NULL, or process only these cells (count in *cell_count)
+    const int *cell_count;
 };
 int launch_cascade_match(const MatchParams &p, cudaStream_t stream);
+
+// ---- match_tile.cu: TMA-tiled correlation for window-structured candidate lists; other cells go to p.fb_list
+size_t match_tile_smem_bytes();
+bool match_tile_applicable(const MatchParams &p);
+int launch_cascade_match_tile(const MatchParams &p, cudaStream_t stream);
 
 // ---- extract.cu
 int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01, const int64_t *next_idx01,

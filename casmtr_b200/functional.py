@@ -211,10 +211,12 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
         'next_idx10': torch.empty(B, L1, dtype=torch.int64, device=dev),
     }
     with torch.cuda.device(dev):
+        ws = _workspace(lib().casmtr_cascade_match_workspace_bytes(B, L0, L1), dev)
         check(lib().casmtr_cascade_match_fwd(_ptr(feat0), _ptr(feat1), _ptr(idx01), _ptr(idx10), _ptr(m0), _ptr(m1),
                                              float(temperature), _ptr(o['conf01']), _ptr(o['next_conf01']), _ptr(o['next_idx01']),
                                              _ptr(o['conf10']), _ptr(o['next_conf10']), _ptr(o['next_idx10']),
-                                             B, L0, L1, Cc, K, int(w0), int(w1), _stream(feat0)), 'casmtr_cascade_match_fwd')
+                                             B, L0, L1, Cc, K, int(w0), int(w1), _ptr(ws), ws.numel(), _stream(feat0)),
+              'casmtr_cascade_match_fwd')
     return o
 
 

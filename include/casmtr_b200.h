@@ -164,13 +164,20 @@ CASMTR_API int casmtr_cascade_qtatt_fwd(const float *query, const float *key, co
  * w0 / w1: row length of the image-0 / image-1 token grids, or 0 if unknown.  With even grids the kernel
  * processes the 2x2 sibling tokens of a parent cell together and, when their candidate lists are identical
  * (they are when idx comes from CascadeQTAttB's upsampled_idx), reads every candidate row once for all four;
- * results do not depend on w0 / w1. */
+ * results do not depend on w0 / w1.
+ * workspace: casmtr_cascade_match_workspace_bytes() bytes, or NULL.  With a workspace, K == 100, no masks and 16-byte
+ * aligned inputs, cells whose lists are the regular 10x10 window of a CascadeQTAttB upsampled_idx are served by the
+ * TMA-tiled kernel (match_tile.cu); all other cells, and every call without a workspace, by the gather kernels. */
+/* Bytes of workspace casmtr_cascade_match_fwd wants (the tile kernel's fallback cell list). */
+CASMTR_API size_t casmtr_cascade_match_workspace_bytes(int B, int L0, int L1);
+
 CASMTR_API int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
                              const int64_t *idx01, const int64_t *idx10,
                              const uint8_t *mask0, const uint8_t *mask1, float temperature,
                              float *conf01, float *next_conf01, int64_t *next_idx01,
                              float *conf10, float *next_conf10, int64_t *next_idx10,
-                             int B, int L0, int L1, int C, int K, int w0, int w1, casmtr_stream_t stream);
+                             int B, int L0, int L1, int C, int K, int w0, int w1,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS + match extraction (R7) */
 

@@ -44,7 +44,7 @@ def test_argument_validation_needs_no_gpu():
     assert rc == -2
     with pytest.raises(_lib.CasmtrError):
         _lib.check(rc, 'casmtr_score3d_fwd')
-    rc = lib.casmtr_cascade_match_fwd(None, None, None, None, None, None, 1.0, None, None, None, None, None, None, 1, 4, 4, 8, 4, 0, 0, None)
+    rc = lib.casmtr_cascade_match_fwd(None, None, None, None, None, None, 1.0, None, None, None, None, None, None, 1, 4, 4, 8, 4, 0, 0, None, 0, None)
     assert rc == -1                                                                  # null pointers
 
 
