@@ -37,7 +37,65 @@ __global__ void __launch_bounds__(256) transpose_jobs_kernel(TransposeJobs jobs)
     }
 }
 
+// Vectorised variant (every map has C % 32 == 0 and HW % 16 == 0): no shared memory at all.  One warp moves a
+// 32-channel x 16-token block: lane = (channel group cg = lane & 7, token quad tq = lane >> 3) loads one float4 (4 tokens)
+// from each of its 4 channels -- 64-byte contiguous pieces per channel -- transposes the 4x4 block in registers and
+// stores 4 float4, one per token; for a fixed token the 8 channel groups of a warp write one full 128-byte line.
+// 8 memory instructions per 16 elements per thread: the scalar tile kernel above is issue-bound (ncu: 77 % issue
+// active at 3.6 TB/s), this one is HBM-bound.
+struct VecJobs {
+    TransposeJob job[12];
+    int blk_begin[13];          // first 32ch x 128tok block of every job (a CTA = 8 warps = 128 tokens)
+    int n;
+};
+
+__global__ void __launch_bounds__(256) transpose_vec_kernel(VecJobs jobs) {
+    int t = blockIdx.x;
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < jobs.n && t >= jobs.blk_begin[j + 1]) ++j;
+    const TransposeJob jb = jobs.job[j];
+    t -= jobs.blk_begin[j];
+    const int cblocks = jb.C >> 5;
+    const int cb = t % cblocks, tb = t / cblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = lane & 7, tq = lane >> 3;
+    const int tok = tb * 128 + warp * 16 + tq * 4;
+    if (tok >= jb.HW) return;
+    const int c0 = cb * 32 + cg * 4;
+    const size_t b = blockIdx.y;
+    const float *src = jb.src + b * (size_t)jb.C * jb.HW + (size_t)c0 * jb.HW + tok;
+    float *dst = jb.dst + b * (size_t)jb.C * jb.HW + (size_t)tok * jb.C + c0;
+    const float4 r0 = ldg4_stream(src), r1 = ldg4_stream(src + jb.HW), r2 = ldg4_stream(src + 2 * (size_t)jb.HW),
+                 r3 = ldg4_stream(src + 3 * (size_t)jb.HW);
+    *reinterpret_cast<float4 *>(dst) = make_float4(r0.x, r1.x, r2.x, r3.x);
+    *reinterpret_cast<float4 *>(dst + jb.C) = make_float4(r0.y, r1.y, r2.y, r3.y);
+    *reinterpret_cast<float4 *>(dst + 2 * (size_t)jb.C) = make_float4(r0.z, r1.z, r2.z, r3.z);
+    *reinterpret_cast<float4 *>(dst + 3 * (size_t)jb.C) = make_float4(r0.w, r1.w, r2.w, r3.w);
+}
+
 int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
+    bool vec = true;
+    for (int i = 0; i < jobs.n; ++i)
+        vec = vec && jobs.job[i].C % 32 == 0 && jobs.job[i].HW % 4 == 0 &&
+              (((uintptr_t)jobs.job[i].src | (uintptr_t)jobs.job[i].dst) & 15) == 0;
+    if (vec && jobs.n > 0 && B > 0) {
+        VecJobs vj;
+        vj.n = jobs.n;
+        int total = 0;
+        for (int i = 0; i < jobs.n; ++i) {
+            vj.job[i] = jobs.job[i];
+            vj.blk_begin[i] = total;
+            total += (jobs.job[i].C / 32) * ((jobs.job[i].HW + 127) / 128);
+        }
+        vj.blk_begin[jobs.n] = total;
+        if (total == 0) return CASMTR_OK;
+        LaunchScope ls(CASMTR_K_LAYOUT, stream);
+        transpose_vec_kernel<<<dim3(total, B), 256, 0, stream>>>(vj);
+        CASMTR_CHECK_LAUNCH("transpose_vec_kernel");
+        return CASMTR_OK;
+    }
+
     int total = 0;
     for (int i = 0; i < jobs.n; ++i) {
         jobs.job[i].tile_begin = total;

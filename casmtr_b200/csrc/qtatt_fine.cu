@@ -384,6 +384,233 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
 #undef QTOK
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// QTAtt fine levels, CTA-per-item variant: 4 warps = the 4 sibling queries of one (parent, head).  The K / V / Q slab is
+// shared by the CTA, so shared memory is spent per ITEM while the warp count is 4x that of the warp-per-item kernel:
+// 13 (kp = 16) or 6 (kp = 32) resident items per SM = 52 / 24 warps instead of 12 / 6, which is what these latency-bound
+// gathers need.  Each warp: issues a quarter of the item's cp.async gathers, then for ITS sibling lane=candidate Q.K^T,
+// softmax, top-k and A.V.  Top-k needs no shared memory and no sort: T = k-th largest of the 32 lane maxima (rank
+// counting), survivors {score >= T} (n >= k, typically n - k < 8) are trimmed by removing the minimum n - k times, and
+// the k remaining candidates are emitted in candidate order (the reference's torch.topk order is by score; only the SET
+// is consumed downstream, and every comparison in tests/ is on sets).
+template <int KP, int R, bool TYPE_A, bool DO_TOPK>
+__global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;       // warp = sibling f
+    const int g = lane >> 3, dq = lane & 7;
+    const int wp = p.w0 >> 1;
+    const int Np = (p.h0 >> 1) * wp;
+    const int b = blockIdx.y;
+    const int parent = blockIdx.x / (unsigned)p.nh, h = blockIdx.x - parent * p.nh;
+    const int py = parent / wp, px = parent - py * wp;
+    const int C = p.nh * D, L0 = p.h0 * p.w0, L1 = p.h1 * p.w1;
+    const int kp = KP ? KP : p.kp, KC = 4 * kp;
+    const float scale = rsqrtf((float)D);
+
+    float *Ks = smem;                                          // [max(KC,32)][32], chunk-swizzled
+    float *Vs = Ks + (KC < 32 ? 32 : KC) * D;                  // [KC][32]
+    float *Qs = Vs + KC * D;                                   // [4][32]
+    float *As = Qs + 4 * D;                                    // [4][KC] attention weights, one row per sibling
+
+    // ---- candidate bases: lane k (< kp) holds the top-left child of parent-candidate k
+    int base = 0;
+    float pscore = 0.f;
+    if (lane < kp) {
+        const size_t o = (((size_t)b * Np + parent) * p.nh + h) * kp + lane;
+        const int idx = p.prev_idx[o];
+        const int r = idx / p.w_prev;
+        base = 2 * r * p.w1 + 2 * (idx - r * p.w_prev);
+        if (TYPE_A) pscore = p.prev_score[o];
+    }
+    const int off_g = (g >> 1) * p.w1 + (g & 1);
+    const int qtok = (2 * py + (f >> 1)) * p.w0 + 2 * px + (f & 1);     // this warp's query token
+
+    // ---- gathers: warp f takes parent candidates u = f, f+4, ..; warp 0 also the 4 q rows
+    {
+        const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
+        const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
+        if (f == 0) {
+            const int qt = (2 * py + (g >> 1)) * p.w0 + 2 * px + (g & 1);
+            cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + qt) * C + h * D + 4 * dq);
+        }
+        float *kd0 = Ks + g * D + 4 * (dq ^ g), *kd1 = Ks + g * D + 4 * (dq ^ (4 + g));
+        float *vd = Vs + g * D + 4 * dq;
+#pragma unroll
+        for (int i = 0; i < (KP ? (KP + 3) / 4 : 8); ++i) {
+            const int u = 4 * i + f;
+            const int tok = __shfl_sync(FULL_MASK, base, u & 31) + off_g;
+            if (u < kp) {
+                const size_t off = (size_t)tok * C;
+                cp_async16(((u & 1) ? kd1 : kd0) + u * 4 * D, kb + off);
+                cp_async16(vd + u * 4 * D, vb + off);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    // ---- Q.K^T for sibling f, lane = candidate
+    float sc[R];
+    {
+        float2 acc[R];
+        const float *krow[R];
+        int ksw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            acc[r] = make_float2(0.f, 0.f);
+            const int c = min(32 * r + lane, KC - 1);          // rows past KC re-read the last valid row; masked below
+            krow[r] = Ks + c * D;
+            ksw[r] = c & 7;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 qv = *reinterpret_cast<const float4 *>(Qs + f * D + 4 * j);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = dot4p(qv, *reinterpret_cast<const float4 *>(krow[r] + 4 * (j ^ ksw[r])), acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) sc[r] = 32 * r + lane < KC ? (acc[r].x + acc[r].y) * scale : -INFINITY;
+    }
+
+    // ---- softmax -> a[r]; sel[r] = selection score (>= 0) or -1
+    float a[R], sel[R];
+    if (!TYPE_A) {
+        float m = sc[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) m = fmaxf(m, sc[r]);
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { a[r] = exp_neg(sc[r] - m); sum += a[r]; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { a[r] *= inv; sel[r] = 32 * r + lane < KC ? a[r] : -1.f; }
+    } else {            // QTAttA: over the 4 children of each parent candidate (4 adjacent lanes), times the parent's score (:72-77)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool valid = 32 * r + lane < KC;
+            const float ps = __shfl_sync(FULL_MASK, pscore, (8 * r + (lane >> 2)) & 31);
+            float m = sc[r];
+            m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
+            const float e = valid ? exp_neg(sc[r] - m) : 0.f;
+            float sum = e;
+            sum += __shfl_xor_sync(FULL_MASK, sum, 1);
+            sum += __shfl_xor_sync(FULL_MASK, sum, 2);
+            a[r] = valid ? (e / sum) * ps : 0.f;
+            sel[r] = valid ? a[r] : -1.f;
+        }
+    }
+
+    // ---- top-k of sibling f for the next level
+    if (DO_TOPK) {
+        const int k = p.topk;
+        unsigned key[R], km = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { key[r] = okey(sel[r]); km = max(km, key[r]); }
+        int above = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) above += __shfl_sync(FULL_MASK, km, l) > km;
+        const unsigned T = __reduce_min_sync(FULL_MASK, (above < k && km > 0) ? km : 0xffffffffu);   // k-th largest lane maximum
+        int n = 0;
+        bool sv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            sv[r] = key[r] >= T && key[r] > 0;
+            n += __popc(__ballot_sync(FULL_MASK, sv[r]));
+        }
+        while (n > k) {                              // drop the smallest survivor (ties: lowest lane, lowest round)
+            unsigned lm = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) lm = min(lm, sv[r] ? key[r] : 0xffffffffu);
+            const unsigned gm = __reduce_min_sync(FULL_MASK, lm);
+            const int owner = __ffs(__ballot_sync(FULL_MASK, lm == gm)) - 1;
+            if (lane == owner) {
+                bool done = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (!done && sv[r] && key[r] == gm) { sv[r] = false; done = true; }
+            }
+            --n;
+        }
+        // emit in candidate order
+        int slot0 = 0;
+        const size_t o0 = (((size_t)b * L0 + qtok) * p.nh + h) * k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned bal = __ballot_sync(FULL_MASK, sv[r]);
+            const int c = 32 * r + lane;
+            const int tok = __shfl_sync(FULL_MASK, base, (c >> 2) & 31) + ((c & 3) >> 1) * p.w1 + (c & 1);
+            if (sv[r]) {
+                const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+                p.topk_idx[o0 + slot] = tok;
+                p.topk_score[o0 + slot] = a[r];
+                if (TYPE_A && !p.final_level) a[r] = 0.f;      // selected keys leave the message (:81-84)
+            }
+            slot0 += __popc(bal);
+        }
+    }
+
+    // ---- A.V for sibling f: lane = (child slot g, chunk dq)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (32 * r + lane < KC) As[f * KC + 32 * r + lane] = a[r];
+    __syncwarp();
+    float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+    {
+        const float *arow = As + f * KC + g;
+        const float *vrow = Vs + g * D + 4 * dq;
+#pragma unroll
+        for (int u = 0; u < (KP ? KP : 32); ++u) {
+            if (KP == 0 && u >= kp) break;
+            const float4 vv = *reinterpret_cast<const float4 *>(vrow + u * 4 * D);
+            const float aw = arow[4 * u];
+            o0 = __ffma2_rn(make_float2(aw, aw), make_float2(vv.x, vv.y), o0);
+            o1 = __ffma2_rn(make_float2(aw, aw), make_float2(vv.z, vv.w), o1);
+        }
+    }
+    float4 res = make_float4(o0.x, o0.y, o1.x, o1.y);
+#pragma unroll
+    for (int m = 8; m <= 16; m <<= 1) {
+        res.x += __shfl_xor_sync(FULL_MASK, res.x, m); res.y += __shfl_xor_sync(FULL_MASK, res.y, m);
+        res.z += __shfl_xor_sync(FULL_MASK, res.z, m); res.w += __shfl_xor_sync(FULL_MASK, res.w, m);
+    }
+    // ---- merge with the coarser levels and write raster (:262-284)
+    if (g == 0) {
+        const float wl = p.wsm ? __ldg(p.wsm + p.level) : 1.f;
+        res.x *= wl; res.y *= wl; res.z *= wl; res.w *= wl;
+        if (p.acc_prev) {
+            const float4 ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
+            res.x += ap.x; res.y += ap.y; res.z += ap.z; res.w += ap.w;
+        }
+        *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + qtok) * C + h * D + 4 * dq) = res;
+    }
+}
+
+__host__ __device__ inline int cta_slab_floats(int kp) { return warp_slab_floats(kp) + 16 * kp; }
+
+template <int KP, int R, bool TYPE_A, bool DO_TOPK>
+int launch_cta_t(const FineParams &p, cudaStream_t stream) {
+    const long long items = (long long)(p.h0 / 2) * (p.w0 / 2) * p.nh;       // per batch element
+    if (items == 0 || p.B == 0) return CASMTR_OK;
+    CASMTR_REQUIRE(items <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
+    const size_t smem = sizeof(float) * cta_slab_floats(p.kp);
+    auto kern = quad_cta_kernel<KP, R, TYPE_A, DO_TOPK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        attr_set = true;
+    }
+    LaunchScope ls(DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST, stream);
+    kern<<<dim3((unsigned)items, p.B), 128, smem, stream>>>(p);
+    CASMTR_CHECK_LAUNCH("quad_cta_kernel");
+    return CASMTR_OK;
+}
+
 // grid.x covers the (parent, head) items of one batch element, grid.y = batch
 template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
 __global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int warps_per_cta) {
@@ -458,10 +685,10 @@ int launch_list_t(const FineParams &p, cudaStream_t stream) {
 
 template <int KP, int R>
 int launch_by_flags(const FineParams &p, cudaStream_t stream) {
-    if (p.topk_pos) return launch_t<KP, R, true, false, false>(p, stream);
-    const bool topk = p.topk_idx != nullptr;
-    if (p.type_a) return topk ? launch_t<KP, R, false, true, true>(p, stream) : launch_t<KP, R, false, true, false>(p, stream);
-    return topk ? launch_t<KP, R, false, false, true>(p, stream) : launch_t<KP, R, false, false, false>(p, stream);
+    if (p.topk_pos) return launch_t<KP, R, true, false, false>(p, stream);       // cascade (gather path): warp per item
+    const bool topk = p.topk_idx != nullptr;                                      // QTAtt fine levels: CTA per item
+    if (p.type_a) return topk ? launch_cta_t<KP, R, true, true>(p, stream) : launch_cta_t<KP, R, true, false>(p, stream);
+    return topk ? launch_cta_t<KP, R, false, true>(p, stream) : launch_cta_t<KP, R, false, false>(p, stream);
 }
 
 }  // namespace
