@@ -60,11 +60,21 @@ __device__ __forceinline__ void warp_select_k(float *vals, int n, int k, int lan
 }
 
 // stage one K/V tile (TILE tokens x 32 floats of head h) into smem with 16-byte cp.async; rows past Sk are zero-filled
+// token t of a tile -> XOR mask for its 16-byte chunk index.  With G lane groups per warp (G = 32 / ROWS) reading G
+// different tokens t, t + TPL, .. in one instruction, the groups must land in different bank groups: the group index
+// (t / TPL) % G is spread over the 3 chunk-index bits.
+template <int G>
+__device__ __forceinline__ int tok_swizzle(int t) {
+    constexpr int TPL = (TILE / NW) / G;
+    return G == 1 ? 0 : (((t / TPL) % G) * (8 / G));
+}
+
+template <int G>
 __device__ __forceinline__ void load_tile_async(float *dst, const float *src_head, int tok0, int Sk, int C, int tid) {
     for (int i = tid; i < TILE * 8; i += NW * 32) {
         const int t = i >> 3, c = i & 7;
         const int tok = tok0 + t;
-        float *d = dst + t * D + 4 * (c ^ (((t >> 2) & 1) << 2));     // 16-byte chunk swizzle: tokens t and t+4 (the two lane halves of a 16-row CTA) hit different banks
+        float *d = dst + t * D + 4 * (c ^ tok_swizzle<G>(t));
         if (tok < Sk) __pipeline_memcpy_async(d, src_head + (size_t)tok * C + 4 * c, 16);
         else *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -73,12 +83,12 @@ __device__ __forceinline__ void load_tile_async(float *dst, const float *src_hea
 
 template <int ROWS>
 __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
-    constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16)
+    constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16, 4 for 8)
     constexpr int TOK_PER_WARP = TILE / NW;        // 8
     extern __shared__ __align__(16) float smem[];
     float *KVs = smem;                              // [2][TILE][D]
     float *Ss = KVs + 2 * TILE * D;                 // [ROWS][s_ld]       (aliased by the AV reduction buffer)
-    const int slab_floats = ROWS * s_ld > NW * 32 * RED_LD ? ROWS * s_ld : NW * 32 * RED_LD;
+    const int slab_floats = ROWS * s_ld > NW * ROWS * RED_LD ? ROWS * s_ld : NW * ROWS * RED_LD;
     float *lval = Ss + slab_floats;                 // [NW][LIST_CAP]
     int *lpos = (int *)(lval + NW * LIST_CAP);      // [NW][LIST_CAP]
     float *rsum = (float *)(lpos + NW * LIST_CAP);  // [32] row sums of exp
@@ -97,36 +107,37 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
     const int grow = min(row0 + myrow, p.Sq - 1);   // clamped: out-of-range rows compute garbage that is never stored
 
     // ---- phase 1: scores
-    load_tile_async(KVs, kb, 0, p.Sk, C, tid);
+    load_tile_async<HALVES>(KVs, kb, 0, p.Sk, C, tid);
     float4 q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) q[c] = ldg4(qb + (size_t)grow * C + 4 * c);
     for (int kt = 0; kt < n_tiles; ++kt) {
         float *cur = KVs + (kt & 1) * TILE * D;
-        if (kt + 1 < n_tiles) load_tile_async(KVs + ((kt + 1) & 1) * TILE * D, kb, (kt + 1) * TILE, p.Sk, C, tid);
+        if (kt + 1 < n_tiles) load_tile_async<HALVES>(KVs + ((kt + 1) & 1) * TILE * D, kb, (kt + 1) * TILE, p.Sk, C, tid);
         else __pipeline_commit();
         __pipeline_wait_prior(1);
         __syncthreads();
         // warp w: tokens w*8 .. w*8+7 of the tile; with 16-row CTAs the two lane halves take 4 tokens each
         constexpr int TPL = TOK_PER_WARP / HALVES;  // tokens per lane group
+        constexpr int TB = TPL < 4 ? TPL : 4;       // tokens per inner step (independent accumulation chains)
 #pragma unroll
-        for (int t0 = 0; t0 < TPL; t0 += 4) {
+        for (int t0 = 0; t0 < TPL; t0 += TB) {
             const int tb = warp * TOK_PER_WARP + half * TPL + t0;
-            float2 acc[4];
+            float2 acc[TB];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
-            const int sw = ((tb >> 2) & 1) << 2;        // tb is a multiple of 4: the 4 tokens share the swizzle
+            for (int j = 0; j < TB; ++j) acc[j] = make_float2(0.f, 0.f);
+            const int sw = tok_swizzle<HALVES>(tb);     // the TB tokens of a step belong to one lane group: same swizzle
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < TB; ++j) {
                     const float4 kv = *reinterpret_cast<const float4 *>(cur + (tb + j) * D + 4 * (c ^ sw));
                     acc[j] = __ffma2_rn(make_float2(q[c].x, q[c].y), make_float2(kv.x, kv.y), acc[j]);
                     acc[j] = __ffma2_rn(make_float2(q[c].z, q[c].w), make_float2(kv.z, kv.w), acc[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < TB; ++j) {
                 const int tok = kt * TILE + tb + j;
                 Ss[myrow * s_ld + tok] = tok < p.Sk ? (acc[j].x + acc[j].y) * scale : -INFINITY;
             }
@@ -228,10 +239,10 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
     float2 o[D / 2];
 #pragma unroll
     for (int d = 0; d < D / 2; ++d) o[d] = make_float2(0.f, 0.f);
-    load_tile_async(KVs, vb, 0, p.Sk, C, tid);
+    load_tile_async<HALVES>(KVs, vb, 0, p.Sk, C, tid);
     for (int vt = 0; vt < n_tiles; ++vt) {
         float *cur = KVs + (vt & 1) * TILE * D;
-        if (vt + 1 < n_tiles) load_tile_async(KVs + ((vt + 1) & 1) * TILE * D, vb, (vt + 1) * TILE, p.Sk, C, tid);
+        if (vt + 1 < n_tiles) load_tile_async<HALVES>(KVs + ((vt + 1) & 1) * TILE * D, vb, (vt + 1) * TILE, p.Sk, C, tid);
         else __pipeline_commit();
         __pipeline_wait_prior(1);
         __syncthreads();
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
             const int tl = warp * TOK_PER_WARP + half * TPL + t;
             const float a = Ss[myrow * s_ld + vt * TILE + tl];
             const float2 aa = make_float2(a, a);
-            const int sw = ((tl >> 2) & 1) << 2;
+            const int sw = tok_swizzle<HALVES>(tl);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 vv = *reinterpret_cast<const float4 *>(cur + tl * D + 4 * (c ^ sw));
@@ -251,12 +262,22 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
         }
         __syncthreads();
     }
-    // cross-warp (and cross-half) reduction through smem, aliased onto the score slab
-    float *red = Ss;                                // [NW * HALVES][ROWS][RED_LD]
+    // lane groups of a warp hold partial sums of the same rows: fold them with shuffles, then reduce across warps
+    // through smem (aliased onto the score slab)
 #pragma unroll
-    for (int d = 0; d < D / 2; ++d) {
-        red[((warp * HALVES + half) * ROWS + myrow) * RED_LD + 2 * d] = o[d].x;
-        red[((warp * HALVES + half) * ROWS + myrow) * RED_LD + 2 * d + 1] = o[d].y;
+    for (int m = ROWS; m < 32; m <<= 1)
+#pragma unroll
+        for (int d = 0; d < D / 2; ++d) {
+            o[d].x += __shfl_xor_sync(FULL_MASK, o[d].x, m);
+            o[d].y += __shfl_xor_sync(FULL_MASK, o[d].y, m);
+        }
+    float *red = Ss;                                // [NW][ROWS][RED_LD]
+    if (half == 0) {
+#pragma unroll
+        for (int d = 0; d < D / 2; ++d) {
+            red[(warp * ROWS + myrow) * RED_LD + 2 * d] = o[d].x;
+            red[(warp * ROWS + myrow) * RED_LD + 2 * d + 1] = o[d].y;
+        }
     }
     __syncthreads();
     float w0 = 1.f;
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
         if (row0 + r < p.Sq) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW * HALVES; ++w) s += red[(w * ROWS + r) * RED_LD + d];
+            for (int w = 0; w < NW; ++w) s += red[(w * ROWS + r) * RED_LD + d];
             p.acc[((size_t)b * p.Sq + row0 + r) * C + h * D + d] = (s / rsum[r]) * w0;
         }
     }
@@ -283,37 +304,42 @@ int coarse_s_ld(int Sk) { return ((Sk + TILE - 1) / TILE * TILE) | 1; }     // o
 
 size_t smem_bytes(int Sk, int rows) {
     const size_t slab = (size_t)rows * coarse_s_ld(Sk);
-    const size_t red = (size_t)NW * 32 * RED_LD;                             // aliased onto the slab
+    const size_t red = (size_t)NW * rows * RED_LD;                           // aliased onto the slab
     return sizeof(float) * (2 * TILE * D + (slab > red ? slab : red) + NW * LIST_CAP + 32) + sizeof(int) * NW * LIST_CAP;
 }
 
 }  // namespace
 
-size_t coarse_smem_bytes(int Sk) { return smem_bytes(Sk, 32) <= 227 * 1024 ? smem_bytes(Sk, 32) : smem_bytes(Sk, 16); }
+size_t coarse_smem_bytes(int Sk) { return smem_bytes(Sk, 8); }
 
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
-    // 32-row CTAs are the efficient shape (all lanes own a row); with too few of them to give every SM two, 16-row CTAs
-    // (lane halves split the tokens) spread the same work over twice as many CTAs
-    const long long ctas32 = (long long)((p.Sq + 31) / 32) * p.B * p.nh;
-    const bool rows32 = smem_bytes(p.Sk, 32) <= 227 * 1024 && ctas32 >= 2 * 148;
-    const size_t smem = rows32 ? smem_bytes(p.Sk, 32) : smem_bytes(p.Sk, 16);
+    // 32-row CTAs are the efficient shape (every lane owns a row).  With too few of them to give every SM two, halve the
+    // rows per CTA (lane groups split the tokens).  Measured at 832^2, B = 1 (676 rows x 8 heads): 32 rows 76 us, 16 rows
+    // 58 us, 8 rows 64 us (every CTA streams all K and V tiles, so below 16 rows the tile traffic and barriers dominate).
+    const long long col = (long long)p.B * p.nh;
+    int rows = 32;
+    while (rows > 16 && ((p.Sq + rows - 1) / rows) * col < 2 * 148) rows >>= 1;
+    while (rows > 8 && smem_bytes(p.Sk, rows) > 227 * 1024) rows >>= 1;
+    const size_t smem = smem_bytes(p.Sk, rows);
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED,
-                   "coarsest level has %d keys; the dense level supports at most ~3300 (shared memory)", p.Sk);
+                   "coarsest level has %d keys; the dense level supports at most ~6000 (shared memory)", p.Sk);
     CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= p.Sk, CASMTR_E_INVALID, "coarse top-k %d must be in [1, min(32, %d)]", p.topk, p.Sk);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
         attr_set = true;
     }
-    const int rows = rows32 ? 32 : 16;
     dim3 grid((p.Sq + rows - 1) / rows, p.B * p.nh);
     LaunchScope ls(CASMTR_K_QT_COARSE, stream);
-    if (rows32) qtatt_coarse_kernel<32><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
-    else qtatt_coarse_kernel<16><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    if (rows == 32) qtatt_coarse_kernel<32><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    else if (rows == 16) qtatt_coarse_kernel<16><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    else qtatt_coarse_kernel<8><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
     CASMTR_CHECK_LAUNCH("qtatt_coarse_kernel");
     return CASMTR_OK;
 }
