@@ -119,35 +119,45 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference leg
-def cpu_reference_sample(wl, host, threads):
-    """One full-size call of each kind through the CPU oracle (reference algorithm, torch CPU fp32, all host
-    threads); returns (pairs_per_s extrapolated with the per-pair call counts, seconds spent, detail dict)."""
-    from oracle import cascade as ocas, fine as ofine, qtatt as oqt       # the checker, used here as the CPU baseline
+def cpu_reference_sample(wl, host, threads, sync=None):
+    """One full-size call of each kind through the oracle (reference algorithm in plain torch ops, fp32); returns
+    (pairs_per_s extrapolated with the per-pair call counts, seconds spent, detail dict).  `host` on the CPU = the CPU
+    baseline (all host threads); the same tensors on the GPU (sync = torch.cuda.synchronize) = the "PyTorch on the same
+    GPU" baseline, which is what the reference's own pure-PyTorch QTAttB (quadtree_attention_smart.py) amounts to."""
+    from oracle import cascade as ocas, fine as ofine, qtatt as oqt       # the checker, used here as the baseline
     torch.set_num_threads(threads)
     t = {}
+    _pc = time.perf_counter
+
+    class _Clock:
+        def __call__(self):
+            if sync is not None:
+                sync()
+            return _pc()
+    time_now = _Clock()
     with torch.no_grad():
         c = host['qt'][0]
-        t0 = time.perf_counter()
+        t0 = time_now()
         oqt.qtatt_b(c['q'], c['k'], c['v'], c['weight'], wl.topks, wl.nh8)
-        t['qtatt_b'] = time.perf_counter() - t0
+        t['qtatt_b'] = time_now() - t0
         c = host['cas'][0]
-        t0 = time.perf_counter()
+        t0 = time_now()
         _, idx01 = oqt.cascade_qtatt_b(c['q'], c['k'], c['v'], c['topk_pos'], None, wl.nh4)
-        t['cascade_qtatt_b'] = time.perf_counter() - t0
+        t['cascade_qtatt_b'] = time_now() - t0
         c1 = host['cas'][1]
         idx10 = oqt.quad_to_raster(oqt.cascade_window_idx(c1['topk_pos'], wl.h4, wl.w4).reshape(wl.B, 1, -1, 1, 100)
                                    .expand(wl.B, 1, -1, 4, 100), wl.h4 // 2, wl.w4 // 2).reshape(wl.B, wl.h4 * wl.w4, 100).contiguous()
         m = host['match']
-        t0 = time.perf_counter()
+        t0 = time_now()
         o = ocas.cascade_match(m['feat0'], m['feat1'], idx01, idx10, None, None, 1.0)
         r = ocas.extract_matches(o['next_conf01'], o['next_idx01'], o['next_idx10'], (wl.h4, wl.w4), (wl.h4, wl.w4), (wl.H, wl.W),
                                  test_thr=0.2, border_rm=2, nms_window=5, pre_confs=[(m['pre_conf'], wl.h8, wl.w8)],
                                  pre_thrs=[0.2], double_check=True)
-        t['cascade_matching'] = time.perf_counter() - t0
+        t['cascade_matching'] = time_now() - t0
         M = min(r['mconf'].shape[0], host['fine']['feat_f0'].shape[0])
-        t0 = time.perf_counter()
+        t0 = time_now()
         ofine.fine_match(host['fine']['feat_f0'][:M], host['fine']['feat_f1'][:M], r['mkpts1_c'][:M].float(), wl.H / wl.hf)
-        t['fine_matching'] = time.perf_counter() - t0
+        t['fine_matching'] = time_now() - t0
     per_batch = wl.qt_calls * t['qtatt_b'] + wl.cas_calls * t['cascade_qtatt_b'] + t['cascade_matching'] + t['fine_matching']
     return wl.B / per_batch, sum(t.values()), {k: round(v, 4) for k, v in t.items()} | {'matches': int(M)}
 
@@ -318,14 +328,55 @@ def run_ours(args):
                   'gbps': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6, 1),
                   'frac_of_hbm_peak': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6 / peak, 4)}
 
+    # ---- the same step as a CUDA graph with the two directions of every layer on two streams (extra figure; `value`
+    # stays the sequential eager run whose kernels are timed one by one)
+    graph_info = None
+    if world == 1:
+        try:
+            gr = pipeline.GraphRunner(hp, dev_in, two_streams=True)
+            for _ in range(3):
+                gr.step()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                gout = gr.step()
+            g1.record()
+            torch.cuda.synchronize()
+            g_ms = g0.elapsed_time(g1) / args.steps
+            graph_info = {'value': wl.B / (g_ms / 1000.0), 'unit': UNIT, 'ms_per_step': g_ms, 'matches': int(gout['mconf'].shape[0]),
+                          'what': 'CUDA-graph replay, directions 0->1 / 1->0 of each layer on two streams'}
+            del gr
+        except Exception as e:      # noqa: BLE001
+            graph_info = {'error': str(e)[:300]}
+    host_ms = None
+    if True:        # host-side cost of enqueueing one step (no device wait): how launch-bound the path is
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hp_out = None
+        for i, call in enumerate(dev_in['qt']):
+            hp.run_qt(i, call)
+        for i, call in enumerate(dev_in['cas']):
+            hp.run_cas(i, call)
+        host_ms = (time.perf_counter() - t0) * 1000.0
+        torch.cuda.synchronize()
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config_dict(wl, n_gpus), 'e2e': e2e, 'gpu_launches': int(launches) * args.steps,
         'gpu_launches_per_step': int(launches), 'clocks': clocks, 'roofline': roofline, 'qtatt_call_roofline': qtatt_call,
-        'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'breakdown': breakdown, 'matches_per_step': n_matches,
+        'cuda_graph_2stream': graph_info, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        try:        # the same algorithm as plain torch CUDA ops on this GPU (extra context, not part of the contract)
+            cpu_reference_sample(wl, dev_in, os.cpu_count() or 1, sync=torch.cuda.synchronize)
+            v, spent, detail = cpu_reference_sample(wl, dev_in, os.cpu_count() or 1, sync=torch.cuda.synchronize)
+            line['gpu_torch_baseline'] = {'value': v, 'unit': UNIT, 'seconds_per_call': detail,
+                                          'what': 'oracle (plain torch ops, the formulation of the reference\'s own pure-PyTorch '
+                                                  'QTAttB) on the same GPU, one call of each kind scaled by the call counts'}
+        except Exception as e:      # noqa: BLE001  (out of memory etc.: the figure is optional)
+            line['gpu_torch_baseline'] = {'error': str(e)[:200]}
+        torch.cuda.empty_cache()
         v, spent, detail = cpu_reference_sample(wl, host, os.cpu_count() or 1)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
                                 'sample': SAMPLE_DESC, 'seconds_per_call': detail, 'seconds_spent': round(spent, 2)}

@@ -77,6 +77,7 @@ class CascadeMatching(nn.Module):
         if self.rt is not None or self.rd is not None:
             raise NotImplementedError('ratio tests rt/rd are dead in every shipped config and not implemented')
         self.store_conf_matrix = True       # set False to skip writing the [B,L,K] softmax volume
+        self.defer_sync = False             # True: no host sync in forward (CUDA-graph capture); call finalize(data, level) later
 
     def forward(self, feat_c0, feat_c1, idx_c01, idx_c10, data, mask_c0=None, mask_c1=None,
                 heatmap_c0=None, level='4c', pre_level='8c'):
@@ -100,9 +101,20 @@ class CascadeMatching(nn.Module):
             'next_conf_c01_s': None, 'next_idx_c01_s': None}
         match_result = self.get_coarse_match(o['conf01'], idx_c01, o['next_conf01'], o['next_idx01'], o['next_idx10'],
                                              data, level, pre_level)
+        if self.defer_sync:
+            data[f'stage_{level}']['_deferred'] = match_result
+            return
         data[f'stage_{level}'].update(**match_result)
         if 'm_bids' in match_result:
             data['m_bids'] = match_result['m_bids']
+
+    def finalize(self, data, level='4c'):
+        """Completes a defer_sync forward: reads the match count and fills the match list keys of data[f'stage_{level}']."""
+        r = F.trim_matches(data[f'stage_{level}'].pop('_deferred'))
+        res = {'b_ids': r['b_ids'], 'i_ids': r['i_ids'], 'j_ids': r['j_ids'], 'm_bids': r['b_ids'],
+               'mkpts0_c': r['mkpts0_c'], 'mkpts1_c': r['mkpts1_c'], 'mconf': r['mconf']}
+        data[f'stage_{level}'].update(**res)
+        data['m_bids'] = res['m_bids']
 
     def get_coarse_match(self, conf_matrix01, idx_c01, next_conf_c01, next_idx_c01, next_idx_c10, data, level, pre_level):
         """reference :170-261, 316-331 (inference): one fused, sync-free-until-the-count extraction."""
@@ -116,6 +128,8 @@ class CascadeMatching(nn.Module):
                             pre_confs=pre, pre_thrs=self.pre_thr, double_check=self.double_check,
                             pad_mask0=data[f'mask_{level}0'] if padded else None,
                             pad_mask1=data[f'mask_{level}1'] if padded else None,
-                            scale0=data.get('scale0'), scale1=data.get('scale1'))
+                            scale0=data.get('scale0'), scale1=data.get('scale1'), defer=self.defer_sync)
+        if self.defer_sync:
+            return r
         return {'b_ids': r['b_ids'], 'i_ids': r['i_ids'], 'j_ids': r['j_ids'], 'm_bids': r['b_ids'],
                 'mkpts0_c': r['mkpts0_c'], 'mkpts1_c': r['mkpts1_c'], 'mconf': r['mconf']}

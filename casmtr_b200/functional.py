@@ -222,9 +222,11 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
 
 def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_thr, border_rm, nms_window=None,
                   pre_confs=(), pre_thrs=(), double_check=True, pad_mask0=None, pad_mask1=None,
-                  scale0=None, scale1=None):
+                  scale0=None, scale1=None, defer=False):
     """NMS / thresholds / border / mutual check / ordered compaction.  Same keyword surface as
-    oracle.cascade.extract_matches.  One host sync (the match count), like the reference's torch.where."""
+    oracle.cascade.extract_matches.  One host sync (the match count), like the reference's torch.where.
+    defer=True skips that sync (CUDA-graph capture): the result holds full-capacity buffers plus the device-side
+    'count'; slice them with trim_matches() once the count may be read."""
     _chk(next_conf01, 'next_conf01', torch.float32), _chk(next_idx01, 'next_idx01', torch.int64), _chk(next_idx10, 'next_idx10', torch.int64)
     B, L0 = next_conf01.shape
     dev = next_conf01.device
@@ -268,9 +270,17 @@ def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_
         check(lib().casmtr_match_extract(C.byref(d), _ptr(next_conf01), _ptr(next_idx01), _ptr(next_idx10), _ptr(mask),
                                          _ptr(ids[0]), _ptr(ids[1]), _ptr(ids[2]), _ptr(mconf), _ptr(mk[0]), _ptr(mk[1]),
                                          cap, _ptr(count), _ptr(ws), ws.numel(), _stream(mask)), 'casmtr_match_extract')
-    M = int(count.item())
-    return {'b_ids': ids[0, :M], 'i_ids': ids[1, :M], 'j_ids': ids[2, :M], 'mconf': mconf[:M],
-            'mkpts0_c': mk[0, :M], 'mkpts1_c': mk[1, :M], 'mask': mask.bool()}
+    full = {'b_ids': ids[0], 'i_ids': ids[1], 'j_ids': ids[2], 'mconf': mconf, 'mkpts0_c': mk[0], 'mkpts1_c': mk[1],
+            'mask': mask, 'count': count, '_keep': keep}
+    return full if defer else trim_matches(full)
+
+
+def trim_matches(full):
+    """Reads the match count (host sync) and slices the deferred result of match_extract."""
+    M = min(int(full['count'].item()), full['b_ids'].shape[0])
+    out = {k: full[k][:M] for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0_c', 'mkpts1_c')}
+    out['mask'] = full['mask'].bool()
+    return out
 
 
 def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None):

@@ -184,6 +184,62 @@ class HotPath(nn.Module):
         return out
 
 
+class GraphRunner:
+    """CUDA-graph replay of a step with the model's own concurrency: the two directions of a layer (calls 2i, 2i+1:
+    feat0->feat1 and feat1->feat0, computed from the same inputs in the reference, src/model/modules/transformer.py:300)
+    run on two streams forked/joined inside the graph.  The graph ends before the one host sync of the path (the match
+    count); the fine stage runs eagerly after it.  Inputs are the static device buffers given at capture time."""
+
+    def __init__(self, hp, dev_in, two_streams=True):
+        self.hp, self.dev_in = hp, dev_in
+        dev = dev_in['match']['feat0'].device
+        hp.matching.defer_sync = True
+        try:
+            for _ in range(2):                      # warm-up: function attributes, tensor-map entry point, allocator
+                self._body(None)
+                hp.matching.finalize(self.data)
+            torch.cuda.synchronize(dev)
+            self.side = torch.cuda.Stream(dev) if two_streams else None
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body(self.side)
+            self.deferred = self.data['stage_4c']['_deferred']      # static buffers the graph writes on every replay
+        finally:
+            hp.matching.defer_sync = False
+
+    def _pair(self, fn, n, calls, side):
+        outs = [None] * n
+        main = torch.cuda.current_stream()
+        for i in range(0, n, 2):
+            if side is not None and i + 1 < n:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    outs[i + 1] = fn(i + 1, calls[i + 1])
+                outs[i] = fn(i, calls[i])
+                main.wait_stream(side)
+            else:
+                outs[i] = fn(i, calls[i])
+                if i + 1 < n:
+                    outs[i + 1] = fn(i + 1, calls[i + 1])
+        return outs
+
+    def _body(self, side):
+        hp, d = self.hp, self.dev_in
+        self.qt_out = self._pair(hp.run_qt, len(d['qt']), d['qt'], side)
+        cas = self._pair(hp.run_cas, len(d['cas']), d['cas'], side)
+        idx = [None, None]
+        for i, (_, up) in enumerate(cas):
+            idx[i % 2] = up
+        self.data = hp.run_match(d, idx[0], idx[1])
+
+    @torch.no_grad()
+    def step(self):
+        self.graph.replay()
+        self.data['stage_4c']['_deferred'] = self.deferred
+        self.hp.matching.finalize(self.data)        # host sync: the match count
+        return self.hp.run_fine(self.data, self.dev_in['fine'])
+
+
 class HostFedRunner:
     """End-to-end driver: the step's inputs start in (pinned) HOST memory.  A copy stream uploads each call's inputs
     while the previous calls compute (per-call ready/consumed events), the match list is read back to the host."""

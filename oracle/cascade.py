@@ -47,9 +47,9 @@ def nms_mask(conf, h, w, window, test_thr):
     B = conf.shape[0]
     c = conf.reshape(B, h, w)
     r = window // 2
-    pad = torch.full((B, h + 2 * r, w + 2 * r), float('-inf'), dtype=c.dtype)
+    pad = torch.full((B, h + 2 * r, w + 2 * r), float('-inf'), dtype=c.dtype, device=c.device)
     pad[:, r:r + h, r:r + w] = c
-    keep = torch.ones(B, h, w, dtype=torch.bool)
+    keep = torch.ones(B, h, w, dtype=torch.bool, device=c.device)
     for dy in range(-r, r + 1):
         for dx in range(-r, r + 1):
             if dy == 0 and dx == 0:
@@ -67,10 +67,11 @@ def nearest_upsample(x, h_in, w_in, h_out, w_out):
     """F.interpolate(mode='nearest') of [B,h_in*w_in] to [B,h_out*w_out] (cm.py:201-203):
     src = min(floor(dst * float32(in/out)), in-1)."""
     B = x.shape[0]
-    sy = torch.tensor(h_in / h_out, dtype=torch.float32)
-    sx = torch.tensor(w_in / w_out, dtype=torch.float32)
-    ys = torch.clamp((torch.arange(h_out, dtype=torch.float32) * sy).floor().long(), max=h_in - 1)
-    xs = torch.clamp((torch.arange(w_out, dtype=torch.float32) * sx).floor().long(), max=w_in - 1)
+    dev = x.device
+    sy = torch.tensor(h_in / h_out, dtype=torch.float32, device=dev)
+    sx = torch.tensor(w_in / w_out, dtype=torch.float32, device=dev)
+    ys = torch.clamp((torch.arange(h_out, dtype=torch.float32, device=dev) * sy).floor().long(), max=h_in - 1)
+    xs = torch.clamp((torch.arange(w_out, dtype=torch.float32, device=dev) * sx).floor().long(), max=w_in - 1)
     return x.reshape(B, h_in, w_in)[:, ys][:, :, xs].reshape(B, h_out * w_out)
 
 
@@ -107,8 +108,8 @@ def extract_matches(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, tes
     # border removal on the source grid and on the target coordinate (cf.py:120-172)
     b = border_rm
     if b > 0:
-        ys = torch.arange(h0).reshape(1, h0, 1)
-        xs = torch.arange(w0).reshape(1, 1, w0)
+        ys = torch.arange(h0, device=next_conf01.device).reshape(1, h0, 1)
+        xs = torch.arange(w0, device=next_conf01.device).reshape(1, 1, w0)
         ty = torch.div(next_idx01, w1, rounding_mode='trunc').reshape(B, h0, w0)
         tx = (next_idx01 % w1).reshape(B, h0, w0)
         if pad_mask0 is None:
@@ -124,7 +125,7 @@ def extract_matches(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, tes
 
     if double_check:   # cm.py:244-251: mutual nearest neighbour
         back = torch.gather(next_idx10, 1, next_idx01)
-        mask = mask & (back == torch.arange(L0).unsqueeze(0))
+        mask = mask & (back == torch.arange(L0, device=next_conf01.device).unsqueeze(0))
 
     keep = mask            # flags before the fallback (what the CUDA path reports as mask_out)
     if mask.sum() == 0:   # cm.py:254-255

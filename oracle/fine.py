@@ -28,7 +28,7 @@ def fine_match(feat_f0, feat_f1, mkpts1_c, scale, scale1=None):
     centre = feat_f0[:, WW // 2, :]                                        # :105
     sim = torch.bmm(feat_f1, centre.unsqueeze(-1)).squeeze(-1)             # :106
     heat = torch.softmax(sim * (1.0 / C ** 0.5), dim=1)                    # :107-108
-    grid = normalized_grid(W)
+    grid = normalized_grid(W).to(feat_f0.device)
     coords = heat @ grid                                                   # :111 spatial_expectation2d
     var = heat @ (grid ** 2) - coords ** 2                                 # :115
     std = torch.sqrt(torch.clamp(var, min=1e-10)).sum(-1)                  # :116

@@ -1,8 +1,2 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/r01j_bench.json 2>gpurun_out/r01j_bench.err; tail -3 gpurun_out/r01j_bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r01j_bench.json'))
-print(d['value'], d['ms_per_step'], d['kernel_ms_per_step'], d['matches_per_step'])
-for r in d['breakdown']: print(r)
-PY
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+./scripts/microbench/l2_gather

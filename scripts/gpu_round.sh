@@ -1,23 +1,26 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench (both arms), ncu launch list, ncu --set full of one whole step.
+# One GPU-box pass: parity tests, bench (both arms), ncu launch list, ncu --set full of the main kernels.
 # Run as:  gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh [tag]'
-# Everything lands in gpurun_out/; summaries worth keeping are copied into profiles/ by scripts/summarize_ncu.py.
+# Everything lands in gpurun_out/ (kept under 64 MiB); scripts/ncu_*.py turn the exports into profiles/ summaries.
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
-python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+lscpu | grep -E "Model name|^CPU\(s\)" >> $OUT/${TAG}_gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -3 $OUT/${TAG}_pytest.log
-python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
-cat $OUT/${TAG}_bench.json
-if [ "${SKIP_REF:-0}" != "1" ]; then
-  python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
-  cat $OUT/${TAG}_bench_ref.json
-fi
-if [ "${SKIP_NCU:-0}" != "1" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
-  ncu --set full --clock-control none --import-source on -c 75 -f -o $OUT/${TAG}_step \
-      python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-  ls -la $OUT
-fi
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
+timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
+cat $OUT/${TAG}_bench.json | cut -c1-600
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
+cat $OUT/${TAG}_bench_ref.json | cut -c1-300
+BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|qtatt_coarse|quad_cta|quad_attention_kernel' -c 4 -f -o $OUT/${TAG}_qtatt $BENCH > $OUT/${TAG}_ncu_a.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|cascade_att_tile|quad_attention_list' -s 12 -c 3 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_match|extract_|fine_match' -c 6 -f -o $OUT/${TAG}_match $BENCH > $OUT/${TAG}_ncu_c.log 2>&1
+for r in qtatt cascade match; do
+  ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null
+done
+ls -la $OUT; du -sh $OUT
