@@ -10,7 +10,10 @@ CascadeMatching (2 sparse correlations, softmax/argmax, 5x5 NMS, extraction) + C
 (casmtr_b200/pipeline.py).  A step = one pass of that sequence over one batch of synthetic feature maps.
 
   value      pairs/s with the step's inputs resident in HBM (every call has its own input buffers; one step
-             touches ~0.9 GB > the 126 MB L2, so nothing is served from a previous step's cache lines)
+             touches ~0.9 GB > the 126 MB L2, so nothing is served from a previous step's cache lines).  Two timed
+             passes of K steps each: an eager single-stream pass in which the library brackets every kernel with CUDA
+             events (breakdown / roofline, `value_eager_instrumented`), and the same step replayed as a CUDA graph with
+             the two independent directions of each layer on two streams; `value` is the faster of the two (`execution`)
   e2e        pairs/s through the same module API with the inputs in pinned HOST memory: H2D of every input
              and D2H of the match list inside the timed region (copy stream overlapped with compute)
   roofline   the dominant kernel: algorithmic bytes per launch / its mean device time, CUDA events recorded by
@@ -49,6 +52,7 @@ def parse():
     ap.add_argument('--pairs', type=int, default=1, help='image pairs per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time the eager single-stream path only')
     ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='wall-clock bound of the reference arm')
     return ap.parse_args()
 
@@ -221,6 +225,10 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU leg)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # stdout carries exactly one JSON line: library chatter (NCCL's version banner ...) goes to stderr until then
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     n_gpus = world
@@ -232,11 +240,14 @@ def run_ours(args):
     dev_in = pipeline.tree_map(lambda t: t.to(dev), host)
     pair_offset = rank * wl.B
 
+    cap = wl.fine_cap                                   # static per-rank capacity of the match-list all-gather
+
+    def finish(out):
+        # multi-GPU: the only exchange of the path, one pack kernel + one fixed-size NCCL all-gather, stream ordered
+        return cdist.gather_matches_device(out, pair_offset, cap) if world > 1 else out
+
     def step():
-        out = hp(dev_in)
-        if world > 1:
-            out = cdist.gather_matches(out, pair_offset)
-        return out
+        return finish(hp(dev_in))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -244,33 +255,63 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        """K steps between a barrier + synchronize on both sides, CUDA events on the launch stream, max over ranks."""
+        sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
     for _ in range(max(args.warmup, 3)):
         out = step()
+    if world > 1:
+        out = cdist.unpack_gathered(out)
     n_matches = int(out['mconf'].shape[0])
-
-    # ---- timed region: K steps, CUDA events on the launch stream, library event pairs around every kernel
     sampler = ClockSampler(local)
-    F.profile_collect()
-    sync_all()
     sampler.start()
+
+    # ---- instrumented pass: K eager steps, the library brackets every kernel launch with a CUDA event pair on the launch
+    # stream -> per-kernel device time (roofline, breakdown) and the launch count
+    F.profile_collect()
     l0 = F.launch_count()
     F.profile_enable(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
+    ms_eager = timed(step, args.steps)
     F.profile_enable(False)
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
     launches = (F.launch_count() - l0) // args.steps
     prof = F.profile_collect()
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+
+    # ---- primary pass: the same step replayed as a CUDA graph, the two directions of every layer (independent in the
+    # reference model, transformer.py:300) forked onto two streams; the graph ends at the path's one host sync (the match
+    # count), the fine stage and the multi-GPU all-gather follow eagerly.  Same kernels, same results.
+    graph_info, ms_step, mode = None, ms_eager, 'eager (one stream)'
+    if not args.no_graph:
+        try:
+            gr = pipeline.GraphRunner(hp, dev_in, two_streams=True)
+
+            def gstep():
+                return finish(gr.step())
+            for _ in range(max(args.warmup, 3)):
+                gout = gstep()
+            if world > 1:
+                gout = cdist.unpack_gathered(gout)
+            assert int(gout['mconf'].shape[0]) == n_matches, 'graph replay changed the match list'
+            ms_graph = timed(gstep, args.steps)
+            graph_info = {'ms_per_step': ms_graph, 'matches': n_matches}
+            if ms_graph < ms_eager:
+                ms_step, mode = ms_graph, 'CUDA graph replay, layer directions on two streams'
+            del gr
+        except Exception as e:      # noqa: BLE001  (capture not possible: the eager number stands)
+            graph_info = {'error': str(e)[:300]}
+    clocks = sampler.stop()
     value = wl.B * n_gpus / (ms_step / 1000.0)
 
     # ---- e2e: same module path, inputs from pinned host memory, result read back
@@ -286,7 +327,7 @@ def run_ours(args):
         for _ in range(args.steps):
             res = runner.step()
             if world > 1:
-                cdist.gather_matches({k: v.to(dev) for k, v in res.items() if k != 'expec_f'}, pair_offset)
+                cdist.gather_matches({k: v.to(dev) for k, v in res.items() if k != 'expec_f'}, pair_offset, cap=cap)
         e1.record()
         sync_all()
         wall_ms = (time.perf_counter() - t0) * 1000.0
@@ -328,27 +369,6 @@ def run_ours(args):
                   'gbps': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6, 1),
                   'frac_of_hbm_peak': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6 / peak, 4)}
 
-    # ---- the same step as a CUDA graph with the two directions of every layer on two streams (extra figure; `value`
-    # stays the sequential eager run whose kernels are timed one by one)
-    graph_info = None
-    if world == 1:
-        try:
-            gr = pipeline.GraphRunner(hp, dev_in, two_streams=True)
-            for _ in range(3):
-                gr.step()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(args.steps):
-                gout = gr.step()
-            g1.record()
-            torch.cuda.synchronize()
-            g_ms = g0.elapsed_time(g1) / args.steps
-            graph_info = {'value': wl.B / (g_ms / 1000.0), 'unit': UNIT, 'ms_per_step': g_ms, 'matches': int(gout['mconf'].shape[0]),
-                          'what': 'CUDA-graph replay, directions 0->1 / 1->0 of each layer on two streams'}
-            del gr
-        except Exception as e:      # noqa: BLE001
-            graph_info = {'error': str(e)[:300]}
     host_ms = None
     if True:        # host-side cost of enqueueing one step (no device wait): how launch-bound the path is
         torch.cuda.synchronize()
@@ -365,7 +385,8 @@ def run_ours(args):
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config_dict(wl, n_gpus), 'e2e': e2e, 'gpu_launches': int(launches) * args.steps,
         'gpu_launches_per_step': int(launches), 'clocks': clocks, 'roofline': roofline, 'qtatt_call_roofline': qtatt_call,
-        'cuda_graph_2stream': graph_info, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
+        'execution': mode, 'ms_per_step_eager_instrumented': ms_eager, 'value_eager_instrumented': wl.B * n_gpus / (ms_eager / 1000.0),
+        'cuda_graph': graph_info, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         try:        # the same algorithm as plain torch CUDA ops on this GPU (extra context, not part of the contract)
@@ -382,6 +403,8 @@ def run_ours(args):
                                 'sample': SAMPLE_DESC, 'seconds_per_call': detail, 'seconds_spent': round(spent, 2)}
     else:
         line['cpu_baseline'] = None
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -372,6 +372,14 @@ int casmtr_match_extract(const casmtr_extract_desc *desc,
                                 mkpts0, mkpts1, capacity, count_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf,
+                        const float *mkpts0, const float *mkpts1, int M, int64_t pair_offset, int capacity,
+                        unsigned char *out, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(M >= 0 && capacity >= M && out != nullptr, CASMTR_E_INVALID, "pack_matches: M=%d capacity=%d", M, capacity);
+    CASMTR_REQUIRE(M == 0 || (b_ids && i_ids && j_ids && mconf && mkpts0 && mkpts1), CASMTR_E_INVALID, "pack_matches: null pointer");
+    return launch_pack_matches(b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, M, pair_offset, out, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ fine matching
 int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
                           const float *scale1_b, const int64_t *b_ids, float scale,

@@ -199,6 +199,37 @@ __global__ void __launch_bounds__(BLK) extract_emit_kernel(ExtractArgs a, EmitOu
 
 }  // namespace
 
+// ---- packed match records for the multi-GPU all-gather: row 0 = count, rows 1..M = 44-byte records
+__global__ void pack_matches_kernel(const int64_t *__restrict__ b_ids, const int64_t *__restrict__ i_ids, const int64_t *__restrict__ j_ids,
+                                    const float *__restrict__ mconf, const float *__restrict__ mk0, const float *__restrict__ mk1,
+                                    int M, long long pair_offset, unsigned char *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > M) return;
+    unsigned *w = reinterpret_cast<unsigned *>(out + (size_t)r * 44);          // 44-byte rows are 4-byte aligned
+    if (r == 0) {
+        w[0] = (unsigned)M; w[1] = 0;
+#pragma unroll
+        for (int k = 2; k < 11; ++k) w[k] = 0;
+        return;
+    }
+    const int m = r - 1;
+    const long long b = b_ids[m] + pair_offset, i = i_ids[m], j = j_ids[m];
+    w[0] = (unsigned)b; w[1] = (unsigned)(b >> 32);
+    w[2] = (unsigned)i; w[3] = (unsigned)(i >> 32);
+    w[4] = (unsigned)j; w[5] = (unsigned)(j >> 32);
+    w[6] = __float_as_uint(mconf[m]);
+    w[7] = __float_as_uint(mk0[2 * m]); w[8] = __float_as_uint(mk0[2 * m + 1]);
+    w[9] = __float_as_uint(mk1[2 * m]); w[10] = __float_as_uint(mk1[2 * m + 1]);
+}
+
+int launch_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf, const float *mk0,
+                        const float *mk1, int M, long long pair_offset, unsigned char *out, cudaStream_t stream) {
+    LaunchScope ls(CASMTR_K_EXTRACT, stream);
+    pack_matches_kernel<<<(M + 1 + 255) / 256, 256, 0, stream>>>(b_ids, i_ids, j_ids, mconf, mk0, mk1, M, pair_offset, out);
+    CASMTR_CHECK_LAUNCH("pack_matches_kernel");
+    return CASMTR_OK;
+}
+
 static int extract_blocks(const casmtr_extract_desc &d) {
     return (int)(((size_t)d.B * d.h0 * d.w0 + BLK - 1) / BLK);
 }

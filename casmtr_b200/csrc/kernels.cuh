@@ -98,6 +98,8 @@ int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01,
                          int64_t *j_ids, float *mconf, float *mkpts0, float *mkpts1, int capacity,
                          int32_t *count_out, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t match_extract_workspace(const casmtr_extract_desc &d);
+int launch_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf, const float *mk0,
+                        const float *mk1, int M, long long pair_offset, unsigned char *out, cudaStream_t stream);
 
 // ---- fine_match.cu
 int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, const float *scale1_b,

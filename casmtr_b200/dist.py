@@ -35,13 +35,46 @@ def unpack_matches(buf):
             'mkpts0': fl[:, 1:3], 'mkpts1': fl[:, 3:5]}
 
 
-def gather_matches(m, pair_offset=0, group=None):
+def gather_matches_device(m, pair_offset, cap, group=None):
+    """Stream-ordered variant for CUDA tensors: one pack kernel (libcasmtr_b200) + one fixed-size NCCL all-gather, no host
+    synchronisation.  Returns the gathered blocks [world, cap+1, 44] uint8 on the device; unpack_gathered() turns them
+    into the match dict when the host needs it."""
+    from . import functional as F
+    block = F.pack_matches(m, pair_offset, cap)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return block.unsqueeze(0)
+    allb = torch.empty(world * (cap + 1), RECORD_BYTES, dtype=torch.uint8, device=block.device)
+    dist.all_gather_into_tensor(allb, block, group=group)
+    return allb.reshape(world, cap + 1, RECORD_BYTES)
+
+
+def unpack_gathered(allb):
+    counts = allb[:, 0, :8].reshape(-1).clone().view(torch.int64).tolist()                # the one host read
+    return unpack_matches(torch.cat([allb[r, 1:c + 1] for r, c in enumerate(counts)], dim=0))
+
+
+def gather_matches(m, pair_offset=0, group=None, cap=None):
     """All ranks receive the concatenation (in rank order, i.e. global pair order) of every rank's
-    match list.  Without an initialised process group this is the identity."""
+    match list.  Without an initialised process group this is the identity.
+    cap: static per-rank capacity (>= any rank's match count).  With it the exchange is ONE fixed-size all-gather
+    (row 0 of every rank's block carries its count) and one host read; without it the counts are exchanged first."""
     buf = pack_matches(m, pair_offset)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return unpack_matches(buf)
     world = dist.get_world_size(group)
+    if cap is not None:
+        n = buf.shape[0]
+        if n > cap:
+            raise RuntimeError(f'gather_matches: {n} matches exceed the static capacity {cap}')
+        block = torch.zeros(cap + 1, RECORD_BYTES, dtype=torch.uint8, device=buf.device)
+        block[0, :8] = torch.tensor([n], dtype=torch.int64, device=buf.device).view(torch.uint8)
+        block[1:n + 1] = buf
+        allb = torch.empty(world * (cap + 1), RECORD_BYTES, dtype=torch.uint8, device=buf.device)
+        dist.all_gather_into_tensor(allb, block, group=group)
+        allb = allb.reshape(world, cap + 1, RECORD_BYTES)
+        counts = allb[:, 0, :8].reshape(-1).clone().view(torch.int64).tolist()               # the one host read
+        return unpack_matches(torch.cat([allb[r, 1:c + 1] for r, c in enumerate(counts)], dim=0))
     count = torch.tensor([buf.shape[0]], dtype=torch.int64, device=buf.device)
     counts = [torch.zeros_like(count) for _ in range(world)]
     dist.all_gather(counts, count, group=group)

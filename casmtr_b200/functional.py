@@ -283,6 +283,21 @@ def trim_matches(full):
     return out
 
 
+def pack_matches(m, pair_offset, cap):
+    """dict(b_ids,i_ids,j_ids,mconf,mkpts0,mkpts1) of M matches -> uint8 [cap+1, 44] block (row 0 = count), one kernel."""
+    M = int(m['b_ids'].shape[0])
+    if M > cap:
+        raise RuntimeError(f'pack_matches: {M} matches exceed the static capacity {cap}')
+    dev = m['b_ids'].device
+    out = torch.empty(cap + 1, 44, dtype=torch.uint8, device=dev)
+    t = [_chk(m[k].contiguous(), k, dt) for k, dt in (('b_ids', torch.int64), ('i_ids', torch.int64), ('j_ids', torch.int64),
+                                                      ('mconf', torch.float32), ('mkpts0', torch.float32), ('mkpts1', torch.float32))]
+    with torch.cuda.device(dev):
+        check(lib().casmtr_pack_matches(*[_ptr(x) for x in t], M, int(pair_offset), int(cap), _ptr(out), _stream(out)),
+              'casmtr_pack_matches')
+    return out
+
+
 def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None):
     """-> (expec_f [M,3], mkpts1_f [M,2])."""
     _chk(feat_f0, 'feat_f0', torch.float32), _chk(feat_f1, 'feat_f1', torch.float32)

@@ -212,6 +212,13 @@ CASMTR_API int casmtr_match_extract(const casmtr_extract_desc *desc,
                          int capacity, int32_t *count_out,
                          void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* Packs a match list for the multi-GPU exchange (the reference gathers pickled result dicts over gloo,
+ * src/utils/comm.py:180-220): out [(capacity+1) x 44 bytes]; row 0 = count (int64 little endian), rows 1..M =
+ * {b_id + pair_offset, i_id, j_id : int64; mconf, mkpts0[2], mkpts1[2] : fp32}.  Rows past M are left untouched. */
+CASMTR_API int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf,
+                        const float *mkpts0, const float *mkpts1, int M, int64_t pair_offset, int capacity,
+                        unsigned char *out, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- fine matching (R8) */
 
 /* feat_f0/feat_f1 [M,WW,C]; mkpts1_c [M,2]; scale = hw0_i[0]/hw0_f[0]; scale1_b NULL or [B,2] with

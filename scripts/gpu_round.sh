@@ -14,9 +14,9 @@ timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $O
 cat $OUT/${TAG}_bench.json | cut -c1-600
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
 cat $OUT/${TAG}_bench_ref.json | cut -c1-300
-BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $OUT/${TAG}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|qtatt_coarse|quad_cta|quad_attention_kernel' -c 4 -f -o $OUT/${TAG}_qtatt $BENCH > $OUT/${TAG}_ncu_a.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|cascade_att_tile|quad_attention_list' -s 12 -c 3 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_match|extract_|fine_match' -c 6 -f -o $OUT/${TAG}_match $BENCH > $OUT/${TAG}_ncu_c.log 2>&1

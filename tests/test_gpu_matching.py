@@ -125,3 +125,21 @@ def test_fine_matching_module_empty(dev):
                          'mconf': torch.zeros(0, device=dev), 'b_ids': torch.zeros(0, dtype=torch.long, device=dev)}}
     mod(torch.zeros(0, 25, 64, device=dev), torch.zeros(0, 25, 64, device=dev), data)
     assert data['expec_f'].shape == (0, 3)
+
+
+def test_pack_matches_kernel(dev):
+    """The packed all-gather block written by the library == the torch reference packing (casmtr_b200.dist.pack_matches)."""
+    from casmtr_b200 import dist as cdist
+    g = torch.Generator().manual_seed(3)
+    M, cap = 37, 64
+    m = {'b_ids': torch.randint(0, 3, (M,), generator=g).sort()[0], 'i_ids': torch.randint(0, 9999, (M,), generator=g),
+         'j_ids': torch.randint(0, 9999, (M,), generator=g), 'mconf': torch.rand(M, generator=g),
+         'mkpts0': torch.rand(M, 2, generator=g) * 800, 'mkpts1': torch.rand(M, 2, generator=g) * 800}
+    block = F.pack_matches({k: v.to(dev) for k, v in m.items()}, pair_offset=5, cap=cap).cpu()
+    assert block.shape == (cap + 1, 44)
+    assert int(block[0, :8].clone().view(torch.int64)) == M
+    assert torch.equal(block[1:M + 1], cdist.pack_matches(m, pair_offset=5))
+    back = cdist.unpack_gathered(block.unsqueeze(0))
+    assert torch.equal(back['b_ids'], m['b_ids'] + 5) and torch.equal(back['mkpts1'], m['mkpts1'])
+    empty = F.pack_matches({k: v[:0].to(dev) for k, v in m.items()}, pair_offset=0, cap=4).cpu()
+    assert int(empty[0, :8].clone().view(torch.int64)) == 0
