@@ -29,8 +29,8 @@ def pack_matches(m, pair_offset=0):
 
 def unpack_matches(buf):
     M = buf.shape[0]
-    ids = buf[:, :24].contiguous().view(torch.int64).reshape(M, 3)
-    fl = buf[:, 24:].contiguous().view(torch.float32).reshape(M, 5)
+    ids = buf[:, :24].reshape(-1).clone().view(torch.int64).reshape(M, 3)
+    fl = buf[:, 24:].reshape(-1).clone().view(torch.float32).reshape(M, 5)
     return {'b_ids': ids[:, 0], 'i_ids': ids[:, 1], 'j_ids': ids[:, 2], 'mconf': fl[:, 0],
             'mkpts0': fl[:, 1:3], 'mkpts1': fl[:, 3:5]}
 
