@@ -68,10 +68,11 @@ __device__ __forceinline__ float4 ldg4_stream(const float *p) {
     return r;
 }
 
+// warp-wide fp32 max in ONE instruction: redux.sync.max.f32 (CREDUX.MAX.F32, sm_100a) instead of a 5-step shuffle chain
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -83,6 +83,14 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     int *lpos = (int *)(Ks + 8 * KC + 192);                    // [64] survivor candidate positions
     int *stg_idx = (int *)Qs;                                  // [4][32] top-k token indices
 
+    const int off_g = (g >> 1) * p.dil * p.w1 + (g & 1) * p.dil;
+    const int qtok0 = 2 * py * p.w0 + 2 * px;      // sibling f of the parent is query token qtok0 + (f>>1)*w0 + (f&1)
+#define QTOK(f) (qtok0 + ((f) >> 1) * p.w0 + ((f) & 1))
+    // everything that does not depend on the candidate list goes out first: the q rows and the coarser levels' message
+    cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq);
+    float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.acc_prev) ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
+
     // ---- candidate bases: lane k (< kp) holds the top-left child of parent-candidate k
     int base = 0;
     float pscore = 0.f;
@@ -98,15 +106,11 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
             if (TYPE_A) pscore = p.prev_score[o];
         }
     }
-    const int off_g = (g >> 1) * p.dil * p.w1 + (g & 1) * p.dil;
-    const int qtok0 = 2 * py * p.w0 + 2 * px;      // sibling f of the parent is query token qtok0 + (f>>1)*w0 + (f&1)
-#define QTOK(f) (qtok0 + ((f) >> 1) * p.w0 + ((f) & 1))
 
-    // ---- issue every gather of this item: Q (1 instruction), K and V rows (2 per parent candidate)
+    // ---- issue every K / V gather of this item (2 per parent candidate)
     {
         const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
         const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
-        cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq);
         // row 4u+g lands at chunk dq ^ ((4u+g) & 7) = dq ^ (4*(u&1) + g)
         float *kd0 = Ks + g * D + 4 * (dq ^ g), *kd1 = Ks + g * D + 4 * (dq ^ (4 + g));
         float *vd = Vs + g * D + 4 * dq;
@@ -363,10 +367,7 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     // ---- merge with the coarser levels and write raster (:262-284)
     const float wl = p.wsm ? __ldg(p.wsm + p.level) : 1.f;      // softmax(weight)[level], normalised once by the coarse kernel
     float4 res = make_float4(m4[0] * wl, m4[1] * wl, m4[2] * wl, m4[3] * wl);
-    if (p.acc_prev) {
-        const float4 ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
-        res.x = ap.x + res.x; res.y = ap.y + res.y; res.z = ap.z + res.z; res.w = ap.w + res.w;
-    }
+    res.x = ap.x + res.x; res.y = ap.y + res.y; res.z = ap.z + res.z; res.w = ap.w + res.w;
     *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq) = res;
 
     // ---- cascade: the window's key indices for the 4 children (the reference's upsampled_idx, :450)
@@ -412,6 +413,16 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
     float *Qs = Vs + KC * D;                                   // [4][32]
     float *As = Qs + 4 * D;                                    // [4][KC] attention weights, one row per sibling
 
+    const int off_g = (g >> 1) * p.w1 + (g & 1);
+    const int qtok = (2 * py + (f >> 1)) * p.w0 + 2 * px + (f & 1);     // this warp's query token
+    // independent of the candidate list: the q rows (warp 0) and the coarser levels' message go out first
+    if (f == 0) {
+        const int qt = (2 * py + (g >> 1)) * p.w0 + 2 * px + (g & 1);
+        cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + qt) * C + h * D + 4 * dq);
+    }
+    float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.acc_prev && g == 0) ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
+
     // ---- candidate bases: lane k (< kp) holds the top-left child of parent-candidate k
     int base = 0;
     float pscore = 0.f;
@@ -422,17 +433,11 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
         base = 2 * r * p.w1 + 2 * (idx - r * p.w_prev);
         if (TYPE_A) pscore = p.prev_score[o];
     }
-    const int off_g = (g >> 1) * p.w1 + (g & 1);
-    const int qtok = (2 * py + (f >> 1)) * p.w0 + 2 * px + (f & 1);     // this warp's query token
 
-    // ---- gathers: warp f takes parent candidates u = f, f+4, ..; warp 0 also the 4 q rows
+    // ---- gathers: warp f takes parent candidates u = f, f+4, ..
     {
         const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
         const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
-        if (f == 0) {
-            const int qt = (2 * py + (g >> 1)) * p.w0 + 2 * px + (g & 1);
-            cp_async16(Qs + g * D + 4 * dq, p.q + ((size_t)b * L0 + qt) * C + h * D + 4 * dq);
-        }
         float *kd0 = Ks + g * D + 4 * (dq ^ g), *kd1 = Ks + g * D + 4 * (dq ^ (4 + g));
         float *vd = Vs + g * D + 4 * dq;
 #pragma unroll
@@ -581,10 +586,7 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
     if (g == 0) {
         const float wl = p.wsm ? __ldg(p.wsm + p.level) : 1.f;
         res.x *= wl; res.y *= wl; res.z *= wl; res.w *= wl;
-        if (p.acc_prev) {
-            const float4 ap = ldg4(p.acc_prev + ((size_t)b * Np + parent) * C + h * D + 4 * dq);
-            res.x += ap.x; res.y += ap.y; res.z += ap.z; res.w += ap.w;
-        }
+        res.x += ap.x; res.y += ap.y; res.z += ap.z; res.w += ap.w;
         *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + qtok) * C + h * D + 4 * dq) = res;
     }
 }
