@@ -59,7 +59,6 @@ __device__ __forceinline__ void warp_select_k(float *vals, int n, int k, int lan
     }
 }
 
-// stage one K/V tile (TILE tokens x 32 floats of head h) into smem with 16-byte cp.async; rows past Sk are zero-filled
 // token t of a tile -> XOR mask for its 16-byte chunk index.  With G lane groups per warp (G = 32 / ROWS) reading G
 // different tokens t, t + TPL, .. in one instruction, the groups must land in different bank groups: the group index
 // (t / TPL) % G is spread over the 3 chunk-index bits.
@@ -69,29 +68,164 @@ __device__ __forceinline__ int tok_swizzle(int t) {
     return G == 1 ? 0 : (((t / TPL) % G) * (8 / G));
 }
 
+// Per-thread constants of the tile loader: a thread always moves the same two 16-byte chunks of a tile (tokens t0 and
+// t0 + 32, chunk c), so a tile costs it two cp.async and one pointer bump instead of index arithmetic per chunk.
 template <int G>
-__device__ __forceinline__ void load_tile_async(float *dst, const float *src_head, int tok0, int Sk, int C, int tid) {
-    for (int i = tid; i < TILE * 8; i += NW * 32) {
-        const int t = i >> 3, c = i & 7;
-        const int tok = tok0 + t;
-        float *d = dst + t * D + 4 * (c ^ tok_swizzle<G>(t));
-        if (tok < Sk) __pipeline_memcpy_async(d, src_head + (size_t)tok * C + 4 * c, 16);
-        else *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+struct TileLoader {
+    int t0, soff0, doff0, doff1;
+    size_t soff1;
+    __device__ __forceinline__ TileLoader(int tid, int C) {
+        t0 = tid >> 3;
+        const int c = tid & 7;
+        soff0 = t0 * C + 4 * c;
+        soff1 = (size_t)soff0 + (size_t)32 * C;
+        doff0 = t0 * D + 4 * (c ^ tok_swizzle<G>(t0));
+        doff1 = (t0 + 32) * D + 4 * (c ^ tok_swizzle<G>(t0 + 32));
     }
-    __pipeline_commit();
+    // stage tile `tok0 .. tok0 + TILE` of one head (rows past Sk are zero-filled) and commit the group
+    __device__ __forceinline__ void load(float *dst, const float *src_head, int tok0, int Sk, int C) const {
+        const float *src = src_head + (size_t)tok0 * C;
+        if (tok0 + t0 < Sk) __pipeline_memcpy_async(dst + doff0, src + soff0, 16);
+        else *reinterpret_cast<float4 *>(dst + doff0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tok0 + t0 + 32 < Sk) __pipeline_memcpy_async(dst + doff1, src + soff1, 16);
+        else *reinterpret_cast<float4 *>(dst + doff1) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __pipeline_commit();
+    }
+};
+
+// Softmax + exact top-k of RP score rows at once, the row values held in registers (NV per lane, Sk <= 32 * NV).
+// Processing RP rows together gives the scheduler independent dependency chains (the single-row version is bound by
+// LDS / shuffle latency, not by issue slots); keeping the values in registers removes two of the three passes over smem.
+//   srow[rr]: the row's scores in the slab (in: scaled logits, out: unnormalised exp, padding columns zeroed)
+//   returns per row the exp sum; lane < k holds output slot `lane` (value rv, key index ridx)
+template <int NV, int RP>
+__device__ __forceinline__ void rows_softmax_topk(float *const (&srow)[RP], const bool (&live)[RP], int Sk, int s_pad, int k, int lane,
+                                                   float *const (&lv)[RP], int *const (&lp)[RP], float (&sum)[RP], float (&rv)[RP],
+                                                   int (&ridx)[RP]) {
+    float e[RP][NV];
+    float m[RP];
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        m[rr] = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            e[rr][i] = (live[rr] && c < Sk) ? srow[rr][c] : -INFINITY;
+            m[rr] = fmaxf(m[rr], e[rr][i]);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) m[rr] = warp_max(m[rr]);
+    float m1[RP], m2[RP];
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        sum[rr] = 0.f; m1[rr] = -1.f; m2[rr] = -1.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            const float ex = c < Sk ? exp_neg(e[rr][i] - m[rr]) : 0.f;
+            e[rr][i] = c < Sk ? ex : -1.f;
+            sum[rr] += ex;
+            m2[rr] = fmaxf(m2[rr], fminf(m1[rr], ex));       // running two largest
+            m1[rr] = fmaxf(m1[rr], ex);
+            if (live[rr] && c < s_pad) srow[rr][c] = ex;      // padding columns become 0 for the AV tiles
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) sum[rr] = warp_sum(sum[rr]);
+    // T = k-th largest of the 64 lane-top-2 keys (rank counting); at least k entries of the row are >= T
+    unsigned T[RP];
+    {
+        unsigned k1[RP], k2[RP];
+        int c1[RP], c2[RP];
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr) { k1[rr] = key_of(m1[rr]); k2[rr] = key_of(m2[rr]); c1[rr] = c2[rr] = 0; }
+#pragma unroll 4
+        for (int l = 0; l < 32; ++l) {
+#pragma unroll
+            for (int rr = 0; rr < RP; ++rr) {
+                const unsigned a1 = __shfl_sync(FULL_MASK, k1[rr], l), a2 = __shfl_sync(FULL_MASK, k2[rr], l);
+                c1[rr] += (a1 > k1[rr]) + (a2 > k1[rr]);
+                c2[rr] += (a1 > k2[rr]) + (a2 > k2[rr]);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr)
+            T[rr] = __reduce_min_sync(FULL_MASK, c2[rr] < k ? k2[rr] : (c1[rr] < k ? k1[rr] : 0xffffffffu));
+    }
+    // compact the survivors {value >= T} in key order, straight from the registers
+    int n[RP];
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        n[rr] = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const bool pred = key_of(e[rr][i]) >= T[rr] && T[rr] > 0 && e[rr][i] >= 0.f;
+            const unsigned bal = __ballot_sync(FULL_MASK, pred);
+            const int pos = n[rr] + __popc(bal & ((1u << lane) - 1u));
+            if (pred && pos < LIST_CAP) { lv[rr][pos] = e[rr][i]; lp[rr][pos] = lane + 32 * i; }
+            n[rr] += __popc(bal);
+        }
+    }
+    __syncwarp();
+    // rank every survivor (2 per lane) among the survivors: descending value, ties by list position (= key index)
+    float va[RP], vb[RP];
+    int pa[RP], pb[RP], ra[RP], rb[RP];
+    unsigned ka[RP], kb[RP];
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        va[rr] = lane < n[rr] ? lv[rr][lane] : -1.f;
+        vb[rr] = lane + 32 < n[rr] ? lv[rr][lane + 32] : -1.f;
+        pa[rr] = lane < n[rr] ? lp[rr][lane] : 0;
+        pb[rr] = lane + 32 < n[rr] ? lp[rr][lane + 32] : 0;
+        ka[rr] = key_of(va[rr]); kb[rr] = key_of(vb[rr]);
+        ra[rr] = rb[rr] = 0;
+    }
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) {
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr) {
+            const unsigned oa = __shfl_sync(FULL_MASK, ka[rr], l), ob = __shfl_sync(FULL_MASK, kb[rr], l);
+            ra[rr] += (oa > ka[rr] || (oa == ka[rr] && l < lane)) + (ob > ka[rr]);
+            rb[rr] += (oa >= kb[rr]) + (ob > kb[rr] || (ob == kb[rr] && l < lane));
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        rv[rr] = -1.f; ridx[rr] = 0;
+        if (n[rr] <= LIST_CAP && n[rr] >= k) {
+            if (lane < n[rr] && ra[rr] < k) { lv[rr][ra[rr]] = va[rr]; lp[rr][ra[rr]] = pa[rr]; }
+            if (lane + 32 < n[rr] && rb[rr] < k) { lv[rr][rb[rr]] = vb[rr]; lp[rr][rb[rr]] = pb[rr]; }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        if (n[rr] <= LIST_CAP && n[rr] >= k) {
+            if (lane < k) { rv[rr] = lv[rr][lane]; ridx[rr] = lp[rr][lane]; }
+        } else if (live[rr]) {                       // massive ties: exact but slow path on the row itself
+            int rj;
+            warp_select_k(srow[rr], Sk, k, lane, rv[rr], rj);
+            ridx[rr] = rj;
+            __syncwarp();
+            if (lane < k) srow[rr][ridx[rr]] = rv[rr];     // restore
+        }
+    }
+    __syncwarp();
 }
 
 template <int ROWS>
-__global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
+__global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
     constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16, 4 for 8)
     constexpr int TOK_PER_WARP = TILE / NW;        // 8
     extern __shared__ __align__(16) float smem[];
     float *KVs = smem;                              // [2][TILE][D]
     float *Ss = KVs + 2 * TILE * D;                 // [ROWS][s_ld]       (aliased by the AV reduction buffer)
     const int slab_floats = ROWS * s_ld > NW * ROWS * RED_LD ? ROWS * s_ld : NW * ROWS * RED_LD;
-    float *lval = Ss + slab_floats;                 // [NW][LIST_CAP]
-    int *lpos = (int *)(lval + NW * LIST_CAP);      // [NW][LIST_CAP]
-    float *rsum = (float *)(lpos + NW * LIST_CAP);  // [32] row sums of exp
+    float *lval = Ss + slab_floats;                 // [NW][2][LIST_CAP]
+    int *lpos = (int *)(lval + NW * 2 * LIST_CAP);  // [NW][2][LIST_CAP]
+    float *rsum = (float *)(lpos + NW * 2 * LIST_CAP);  // [32] row sums of exp
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y / p.nh, h = blockIdx.y % p.nh;
@@ -107,13 +241,14 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
     const int grow = min(row0 + myrow, p.Sq - 1);   // clamped: out-of-range rows compute garbage that is never stored
 
     // ---- phase 1: scores
-    load_tile_async<HALVES>(KVs, kb, 0, p.Sk, C, tid);
+    const TileLoader<HALVES> loader(tid, C);
+    loader.load(KVs, kb, 0, p.Sk, C);
     float4 q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) q[c] = ldg4(qb + (size_t)grow * C + 4 * c);
     for (int kt = 0; kt < n_tiles; ++kt) {
         float *cur = KVs + (kt & 1) * TILE * D;
-        if (kt + 1 < n_tiles) load_tile_async<HALVES>(KVs + ((kt + 1) & 1) * TILE * D, kb, (kt + 1) * TILE, p.Sk, C, tid);
+        if (kt + 1 < n_tiles) loader.load(KVs + ((kt + 1) & 1) * TILE * D, kb, (kt + 1) * TILE, p.Sk, C);
         else __pipeline_commit();
         __pipeline_wait_prior(1);
         __syncthreads();
@@ -146,8 +281,40 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
     }
 
     // ---- phase 2 + 3: softmax and top-k, warp `warp` owns rows warp, warp+NW, ...
-    float *mylv = lval + warp * LIST_CAP;
-    int *mylp = lpos + warp * LIST_CAP;
+    constexpr int RPW = (ROWS + NW - 1) / NW;        // rows per warp
+    float *mylv = lval + warp * 2 * LIST_CAP;        // two survivor lists per warp (the fast path handles 2 rows at once)
+    int *mylp = lpos + warp * 2 * LIST_CAP;
+    constexpr int RP = RPW < 2 ? 1 : 2;              // rows processed together by the register fast path
+    constexpr int NVF = 24;                          // fast path: Sk <= 768 (24 values per lane)
+    if (s_pad <= 32 * NVF) {
+        for (int j0 = 0; j0 < RPW; j0 += RP) {
+            float *srow[RP], *lvp[RP];
+            int *lpp[RP];
+            bool live[RP];
+            float sum[RP], rv[RP];
+            int ridx[RP], rws[RP];
+#pragma unroll
+            for (int rr = 0; rr < RP; ++rr) {
+                rws[rr] = warp + (j0 + rr) * NW;
+                live[rr] = j0 + rr < RPW && rws[rr] < ROWS && row0 + rws[rr] < p.Sq;
+                srow[rr] = Ss + (live[rr] ? rws[rr] : 0) * s_ld;
+                lvp[rr] = mylv + rr * LIST_CAP;
+                lpp[rr] = mylp + rr * LIST_CAP;
+            }
+            rows_softmax_topk<NVF, RP>(srow, live, p.Sk, s_pad, p.topk, lane, lvp, lpp, sum, rv, ridx);
+#pragma unroll
+            for (int rr = 0; rr < RP; ++rr) {
+                if (!live[rr]) continue;
+                if (lane == 0) rsum[rws[rr]] = sum[rr];
+                if (lane < p.topk) {
+                    const size_t o = (((size_t)b * p.Sq + row0 + rws[rr]) * p.nh + h) * p.topk + lane;
+                    p.topk_idx[o] = ridx[rr];
+                    p.topk_score[o] = rv[rr] / sum[rr];
+                    if (p.type_a) srow[rr][ridx[rr]] = 0.f;      // QTAttA: selected keys leave the message (:37-42)
+                }
+            }
+        }
+    } else
     for (int r = warp; r < ROWS; r += NW) {
         if (row0 + r >= p.Sq) continue;            // warp-uniform
         float *srow = Ss + r * s_ld;
@@ -239,10 +406,10 @@ __global__ void __launch_bounds__(NW * 32) qtatt_coarse_kernel(CoarseParams p, i
     float2 o[D / 2];
 #pragma unroll
     for (int d = 0; d < D / 2; ++d) o[d] = make_float2(0.f, 0.f);
-    load_tile_async<HALVES>(KVs, vb, 0, p.Sk, C, tid);
+    loader.load(KVs, vb, 0, p.Sk, C);
     for (int vt = 0; vt < n_tiles; ++vt) {
         float *cur = KVs + (vt & 1) * TILE * D;
-        if (vt + 1 < n_tiles) load_tile_async<HALVES>(KVs + ((vt + 1) & 1) * TILE * D, vb, (vt + 1) * TILE, p.Sk, C, tid);
+        if (vt + 1 < n_tiles) loader.load(KVs + ((vt + 1) & 1) * TILE * D, vb, (vt + 1) * TILE, p.Sk, C);
         else __pipeline_commit();
         __pipeline_wait_prior(1);
         __syncthreads();
@@ -305,7 +472,7 @@ int coarse_s_ld(int Sk) { return ((Sk + TILE - 1) / TILE * TILE) | 1; }     // o
 size_t smem_bytes(int Sk, int rows) {
     const size_t slab = (size_t)rows * coarse_s_ld(Sk);
     const size_t red = (size_t)NW * rows * RED_LD;                           // aliased onto the slab
-    return sizeof(float) * (2 * TILE * D + (slab > red ? slab : red) + NW * LIST_CAP + 32) + sizeof(int) * NW * LIST_CAP;
+    return sizeof(float) * (2 * TILE * D + (slab > red ? slab : red) + NW * 2 * LIST_CAP + 32) + sizeof(int) * NW * 2 * LIST_CAP;
 }
 
 }  // namespace
