@@ -232,11 +232,15 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             float2 o[4][2];
 #pragma unroll
             for (int f = 0; f < 4; ++f) o[f][0] = o[f][1] = make_float2(0.f, 0.f);
+            // V row of candidate (wy, wx), child g: tile row vbase + 2*wy*TW + 2*wx.  2*wy*TW = 40*wy is a multiple of 8, so the
+            // swizzle (row & 7) depends on wx only: 5 swizzled base pointers per lane, everything else is an immediate offset
             const int vbase = (2 * wy0 + (g >> 1)) * TW + 2 * wx0 + (g & 1);
+            const float *vp[5];
+#pragma unroll
+            for (int wx = 0; wx < 5; ++wx) vp[wx] = Vt + (vbase + 2 * wx) * D + 4 * (dq ^ ((vbase + 2 * wx) & 7));
 #pragma unroll
             for (int u = 0; u < 25; ++u) {
-                const int trow = vbase + 2 * (u / 5) * TW + 2 * (u % 5);
-                const float4 vv = *reinterpret_cast<const float4 *>(Vt + trow * D + 4 * (dq ^ (trow & 7)));
+                const float4 vv = *reinterpret_cast<const float4 *>(vp[u % 5] + 2 * (u / 5) * TW * D);
                 const float4 aw = *reinterpret_cast<const float4 *>(As + (4 * u + g) * 4);
                 const float2 vlo = make_float2(vv.x, vv.y), vhi = make_float2(vv.z, vv.w);
                 o[0][0] = __ffma2_rn(make_float2(aw.x, aw.x), vlo, o[0][0]); o[0][1] = __ffma2_rn(make_float2(aw.x, aw.x), vhi, o[0][1]);

@@ -54,12 +54,20 @@ __device__ __forceinline__ float pick(const float (&x)[R][4], int r, int f) {   
     return f == 0 ? x[r][0] : f == 1 ? x[r][1] : f == 2 ? x[r][2] : x[r][3];
 }
 
-// floats of shared memory one warp needs for kp parent candidates:
+// floats of shared memory per work item for kp parent candidates:
 //   K slab [max(KC,32)][32] (later aliased by A2[KC][8], top-k staging and scratch), V slab [KC][32], Q [4][32]
-__host__ __device__ inline int warp_slab_floats(int kp) {
+__host__ __device__ inline int staged_slab_floats(int kp) {          // K + V + Q (CTA-per-item kernel)
     const int kc = 4 * kp;
     const int krows = kc < 32 ? 32 : kc;
     return krows * D + kc * D + 4 * D;
+}
+// warp-per-item kernel: only K and Q are staged; V rows are streamed straight into registers in the A.V loop (each lane
+// consumes exactly what it loads, so staging V would only cost shared memory -- and shared memory is what caps the
+// number of resident warps of this latency-bound kernel: 8.7 KB instead of 16.9 KB per warp at kp = 16)
+__host__ __device__ inline int warp_slab_floats(int kp) {
+    const int kc = 4 * kp;
+    const int krows = kc < 32 ? 32 : kc;
+    return krows * D + 4 * D;
 }
 
 // KP > 0: compile-time number of parent candidates (gather loops fully unrolled); KP == 0: runtime p.kp
@@ -74,8 +82,7 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     const float scale = rsqrtf((float)D);
 
     // Ks: this warp's slab, [max(KC,32)][32], chunk-swizzled
-    float *Vs = Ks + (KC < 32 ? 32 : KC) * D;                  // [KC][32]
-    float *Qs = Vs + KC * D;                                   // [4][32]
+    float *Qs = Ks + (KC < 32 ? 32 : KC) * D;                  // [4][32]
     // after Q.K^T the K slab and Q are dead and get reused:
     float *A2 = Ks;                                            // [KC][8]: (a0,a0,a1,a1,a2,a2,a3,a3)
     float *stg_sc = Ks + 8 * KC;                               // [4][32] top-k scores        (8*KC + 256 <= max(KC,32)*32)
@@ -107,21 +114,18 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
         }
     }
 
-    // ---- issue every K / V gather of this item (2 per parent candidate)
+    // ---- issue every K gather of this item (one LDGSTS = the 4 children of a parent candidate)
+    const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
     {
         const float *kb = p.k + (size_t)b * L1 * C + h * D + 4 * dq;
-        const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
         // row 4u+g lands at chunk dq ^ ((4u+g) & 7) = dq ^ (4*(u&1) + g)
         float *kd0 = Ks + g * D + 4 * (dq ^ g), *kd1 = Ks + g * D + 4 * (dq ^ (4 + g));
-        float *vd = Vs + g * D + 4 * dq;
 #pragma unroll
         for (int u = 0; u < (KP ? KP : 32); ++u) {
             if (KP == 0 && u >= kp) break;
             int tok = __shfl_sync(FULL_MASK, base, u) + off_g;
             if (CASCADE) tok = min(max(tok, 0), L1 - 1);       // the reference's clamp (:428); QTAtt children are always in range
-            const size_t off = (size_t)tok * C;
-            cp_async16(((u & 1) ? kd1 : kd0) + u * 4 * D, kb + off);
-            cp_async16(vd + u * 4 * D, vb + off);
+            cp_async16(((u & 1) ? kd1 : kd0) + u * 4 * D, kb + (size_t)tok * C);
         }
         cp_async_commit();
     }
@@ -336,7 +340,9 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
 #pragma unroll
     for (int u = 0; u < (KP ? KP : 32); ++u) {
         if (KP == 0 && u >= kp) break;
-        const float4 vv = *reinterpret_cast<const float4 *>(Vs + (4 * u + g) * D + 4 * dq);
+        int vtok = __shfl_sync(FULL_MASK, base, u) + off_g;
+        if (CASCADE) vtok = min(max(vtok, 0), L1 - 1);
+        const float4 vv = ldg4(vb + (size_t)vtok * C);          // streamed: issued ahead by the unrolled loop
         const float4 a01 = *reinterpret_cast<const float4 *>(A2 + (4 * u + g) * 8);
         const float4 a23 = *reinterpret_cast<const float4 *>(A2 + (4 * u + g) * 8 + 4);
         const float2 vlo = make_float2(vv.x, vv.y), vhi = make_float2(vv.z, vv.w);
@@ -591,7 +597,7 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
     }
 }
 
-__host__ __device__ inline int cta_slab_floats(int kp) { return warp_slab_floats(kp) + 16 * kp; }
+__host__ __device__ inline int cta_slab_floats(int kp) { return staged_slab_floats(kp) + 16 * kp; }
 
 template <int KP, int R, bool TYPE_A, bool DO_TOPK>
 int launch_cta_t(const FineParams &p, cudaStream_t stream) {
