@@ -234,7 +234,7 @@ def run_ours(args):
     n_gpus = world
 
     wl = pipeline.Workload(args.size, args.size, pairs=args.pairs)
-    host = pipeline.make_host_inputs(wl, seed=1234 + 1000 * rank, pin=not args.no_e2e)
+    host = pipeline.make_host_inputs(wl, seed=1234 + 1000 * rank)      # HostFedRunner packs its own pinned blocks
     hp = pipeline.HotPath(wl).to(dev)
     hp.load_level_weights(host)
     dev_in = pipeline.tree_map(lambda t: t.to(dev), host)
@@ -350,6 +350,10 @@ def run_ours(args):
         per = ms / n
         alg = wl.bytes_kernel(kind)
         row = {'kind': kind, 'launches_per_step': n / args.steps, 'ms_per_launch': round(per, 5), 'share': round(ms / kernel_ms, 4)}
+        extra = ncu_stats().get(kind)
+        if extra:       # from the committed ncu --set full capture of the same kernels (profiles/issue.json)
+            row['ncu_issue_active_pct'] = extra['issue_active_pct']
+            row['ncu_l2_to_sm_bytes'] = extra['l2_bytes']
         if alg:
             row['alg_bytes_per_launch'] = alg
             row['gbps'] = round(alg / per / 1e6, 1)
@@ -360,7 +364,11 @@ def run_ours(args):
     if dom:
         roofline = {'bound': 'hbm', 'kernel': dom['kind'], 'achieved': dom['gbps'], 'peak': peak, 'unit': 'GB/s',
                     'frac': dom['frac_of_hbm_peak'], 'traffic': ncu_traffic(dom['kind']), 'peak_source': peak_src,
-                    'alg_bytes_per_launch': dom['alg_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch']}
+                    'alg_bytes_per_launch': dom['alg_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
+                    'note': ('dominant kernel by device time.  The kernels of this path are bound by instruction issue / load '
+                             'latency, not by HBM or L2 bandwidth (gathers re-read each row ~16x from L2, measured L2 gather peak '
+                             '15-20 TB/s): see breakdown[].ncu_issue_active_pct and DESIGN.md section 4'),
+                    'ncu_issue_active_pct': dom.get('ncu_issue_active_pct')}
     qt_ms = sum(prof[k][0] for k in ('qt_coarse', 'qt_fine_mid', 'qt_fine_last')) / args.steps / wl.qt_calls
     lay = prof['layout']
     lay_per_launch = lay[0] / max(lay[1], 1)
@@ -411,6 +419,14 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def ncu_stats():
+    path = os.path.join(ROOT, 'profiles', 'issue.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
 
 
 def ncu_traffic(kind):

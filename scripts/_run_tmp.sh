@@ -1,8 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/r01q_bench.json 2>gpurun_out/r01q_bench.err; tail -3 gpurun_out/r01q_bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r01q_bench.json'))
-print(d['value'], d['ms_per_step'], d['execution'], d['value_eager_instrumented'], d['kernel_ms_per_step'])
-for r in d['breakdown']: print(r['kind'], r['ms_per_launch'], r['share'])
-PY
+BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'cascade_att_tile|cascade_match_tile' -c 2 -f -o gpurun_out/r01r_tiles $BENCH > gpurun_out/r01r_ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'quad_cta|quad_attention_kernel' -c 2 -f -o gpurun_out/r01r_fine $BENCH > gpurun_out/r01r_ncu2.log 2>&1
+for r in tiles fine; do ncu -i gpurun_out/r01r_$r.ncu-rep --page raw --csv > gpurun_out/r01r_${r}_raw.csv 2>/dev/null; done
