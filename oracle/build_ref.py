@@ -35,15 +35,21 @@ def build(verbose=False):
     if not available():
         raise RuntimeError(f'reference tree not found at {REF}')
     os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    import concurrent.futures as cf
     from torch.utils import cpp_extension
-    for name, srcs in MODULES.items():
+
+    def one(item):
+        name, srcs = item
         if built(name):
-            continue
+            return name
         d = os.path.join(OUT, name)
         os.makedirs(d, exist_ok=True)
         cpp_extension.load(name=name, sources=srcs, build_directory=d, verbose=verbose, is_python_module=False,
                            extra_include_paths=[QT, SC], extra_cflags=['-O2', '-w'],
                            extra_cuda_cflags=['-O2', '-w', '-gencode', 'arch=compute_100a,code=sm_100a'])
+        return name
+    with cf.ThreadPoolExecutor(max_workers=3) as ex:        # the three extensions build side by side (~4 min on 8 cores)
+        list(ex.map(one, MODULES.items()))
     return OUT
 
 
