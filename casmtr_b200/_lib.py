@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libcasmtr_b200.so')
 MAX_LEVELS = 4
-K_COUNT = 10          # CASMTR_K_COUNT
+K_COUNT = 11          # CASMTR_K_COUNT
 
 c_float_p = C.c_void_p      # raw device addresses (tensor.data_ptr())
 c_i64_p = C.c_void_p
@@ -56,6 +56,9 @@ SIGNATURES = {
                                            c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                  + [C.c_int] * 7 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_cascade_match_workspace_bytes': (C.c_size_t, [C.c_int] * 3),
+    'casmtr_coarse_match_workspace_bytes': (C.c_size_t, [C.c_int] * 4),
+    'casmtr_coarse_match_fwd': (C.c_int, [c_float_p, c_float_p, C.c_float, c_float_p, c_i64_p, c_float_p, c_i64_p]
+                                + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_match_extract_workspace_bytes': (C.c_size_t, [C.POINTER(ExtractDesc)]),
     'casmtr_match_extract': (C.c_int, [C.POINTER(ExtractDesc), c_float_p, c_i64_p, c_i64_p, c_u8_p, c_i64_p, c_i64_p, c_i64_p,
                                        c_float_p, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

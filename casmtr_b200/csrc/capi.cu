@@ -27,7 +27,7 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof_recs;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 const char *const g_kind_names[CASMTR_K_COUNT] = {"layout", "qt_coarse", "qt_fine_mid", "qt_fine_last", "cascade_att",
-                                                  "cascade_match", "extract", "fine_match", "ops", "cascade_fallback"};
+                                                  "cascade_match", "extract", "fine_match", "ops", "cascade_fallback", "coarse_match"};
 }  // namespace
 
 void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot) {
@@ -336,6 +336,24 @@ int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
         p.fb_count = p.fb_list + (size_t)B * (L0 / 4 + L1 / 4) + 1;
     }
     return launch_cascade_match(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ dense coarse matching
+size_t casmtr_coarse_match_workspace_bytes(int B, int L0, int L1, int C) {
+    if (B <= 0 || L0 <= 0 || L1 <= 0 || C <= 0) return 0;
+    return coarse_match_workspace(B, L0, L1, C);
+}
+
+int casmtr_coarse_match_fwd(const float *feat0, const float *feat1, float temperature,
+                            float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                            int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0, CASMTR_E_INVALID, "coarse_match: bad sizes");
+    CASMTR_REQUIRE(feat0 && feat1 && next_conf01 && next_idx01 && next_conf10 && next_idx10 && workspace, CASMTR_E_INVALID,
+                   "coarse_match: null pointer");
+    CASMTR_REQUIRE(temperature > 0.f, CASMTR_E_INVALID, "coarse_match: temperature must be positive");
+    CASMTR_REQUIRE(2 * B <= 65535, CASMTR_E_UNSUPPORTED, "coarse_match: batch too large");
+    return launch_coarse_match(feat0, feat1, temperature, next_conf01, next_idx01, next_conf10, next_idx10, B, L0, L1, C,
+                               workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ extraction

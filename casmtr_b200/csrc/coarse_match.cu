@@ -1,0 +1,324 @@
+// Dense dual-softmax coarse matching statistics on the 5th-generation tensor cores ("next" #1).
+// Reference: CoarseMatching.forward  src/model/functions/coarse_matching.py:40-89
+//   sim = <f0/sqrt(C), f1/sqrt(C)> / T                       [B, L, S]   (468 MB per tensor at 832^2, four of them)
+//   next_conf_c01, next_idx_c01 = max_j softmax_j(sim);  next_conf_c10, next_idx_c10 = max_i softmax_i(sim)
+// The cascade stages consume only those four vectors, so the L x S matrix is never written: one kernel computes, for both
+// directions, the row-wise (max, sum-exp, arg-max) of sim with the GEMM on tcgen05 and the softmax statistics in the
+// epilogue, a second tiny kernel merges the column splits.
+//
+// fp32 accuracy on TF32 tensor cores: kind::tf32 reads fp32 words from shared memory and uses their top 19 bits, so
+// x_hi = x is implicit and x_lo = x - trunc_tf32(x) is precomputed once per feature map; three MMAs per k-step
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) give ~2^-21 relative error -- the arg-max must match the fp32 reference.
+//
+// CTA = 128 rows x a range of 256-column tiles.  Warp 0: TMA producer (4 operand tiles per 32-channel k-block: A_hi, A_lo
+// 128x32 and B_hi, B_lo 256x32 fp32, 128-byte swizzle, 2-stage ring, 96 KB per stage).  Warp 1: TMEM allocation + MMA issue
+// (UMMA 128x256x8, 12 per k-block), accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile n
+// overlaps the MMAs of tile n+1.  Warps 2-5: epilogue, one accumulator row per thread (tcgen05.ld 32x32b), online softmax.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tma.cuh"
+
+namespace {
+
+using namespace tma;
+constexpr int BM = 128, BN = 256, BK = 32;          // rows per CTA, columns per tile, fp32 channels per k-block (= 128 B)
+constexpr int NSTG = 2;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;              // 96 KB
+constexpr int SM_BAR = NSTG * STAGE_BYTES;
+constexpr int SM_TOTAL = SM_BAR + 128;
+
+struct CoarseMaps { CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2]; };      // [direction]: rows = image d, cols = image 1-d
+
+struct CoarseStatParams {
+    float *pmax, *psum;         // [2][nsplit][B * Lmax] partial row statistics (log2 domain)
+    int *parg;
+    int B, L[2], C, nsplit, Lmax;
+    float scale_log2;           // log2(e) / (C * temperature)
+};
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major operand tile [rows][32 fp32] with 128-byte swizzle: 8-row groups are 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(const void *smem_tile) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_tile) >> 4) & 0x3fffull;
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_constant__ CoarseMaps maps, CoarseStatParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + NSTG, *tfull = empty + NSTG, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.z / p.B, b = blockIdx.z % p.B;
+    const int Lr = p.L[dir], Lc = p.L[1 - dir];
+    const int row0 = blockIdx.x * BM;
+    if (row0 >= Lr) return;                                     // the grid is sized for the longer image
+    const int n_tiles = (Lc + BN - 1) / BN;
+    const int t_begin = (int)((long long)n_tiles * blockIdx.y / p.nsplit), t_end = (int)((long long)n_tiles * (blockIdx.y + 1) / p.nsplit);
+    const int KB = p.C / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    }
+    if (warp == 1) {                                            // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int step = 0;
+            for (int t = t_begin; t < t_end; ++t)
+                for (int kb = 0; kb < KB; ++kb, ++step) {
+                    const int s = step % NSTG;
+                    mbar_wait(empty + s, ((step / NSTG) & 1) ^ 1);
+                    uint8_t *st = sm + s * STAGE_BYTES;
+                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    tma_load_3d(st, &maps.a_hi[dir], kb * BK, row0, b, full + s);
+                    tma_load_3d(st + A_BYTES, &maps.a_lo[dir], kb * BK, row0, b, full + s);
+                    tma_load_3d(st + 2 * A_BYTES, &maps.b_hi[dir], kb * BK, t * BN, b, full + s);
+                    tma_load_3d(st + 2 * A_BYTES + B_BYTES, &maps.b_lo[dir], kb * BK, t * BN, b, full + s);
+                }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int step = 0;
+            for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+                const int a = it & 1;
+                mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + a * BN;
+                for (int kb = 0; kb < KB; ++kb, ++step) {
+                    const int s = step % NSTG;
+                    mbar_wait(full + s, (step / NSTG) & 1);
+                    tc_fence_after();
+                    uint8_t *st = sm + s * STAGE_BYTES;
+                    const uint64_t ah = umma_desc(st), al = umma_desc(st + A_BYTES), bh = umma_desc(st + 2 * A_BYTES),
+                                   bl = umma_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {          // UMMA_K = 8 tf32 = 32 bytes: +2 in descriptor address units
+                        umma_tf32(d, ah + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
+                        umma_tf32(d, ah + 2 * k, bl + 2 * k, idesc, 1);
+                        umma_tf32(d, al + 2 * k, bh + 2 * k, idesc, 1);
+                    }
+                    umma_commit(empty + s);                      // smem stage reusable once these MMAs have read it
+                }
+                umma_commit(tfull + a);                          // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue: one accumulator row per thread =================
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int row = row0 + 32 * q + lane;
+        float m = -INFINITY, l = 0.f;
+        int arg = 0;
+        for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+            const int a = it & 1;
+            mbar_wait(tfull + a, (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + a * BN + 32 * c, v);
+                const int col0 = t * BN + 32 * c;
+                float cm = -INFINITY;
+                int ca = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = col0 + i < Lc ? v[i] * p.scale_log2 : -INFINITY;
+                    if (v[i] > cm) { cm = v[i]; ca = i; }
+                }
+                if (cm > m) { l *= exp2f(m - cm); m = cm; arg = col0 + ca; }
+                if (m > -INFINITY) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) l += exp2f(v[i] - m);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + a);
+        }
+        if (row < Lr) {
+            const size_t o = ((size_t)(dir * p.nsplit + blockIdx.y) * p.B + b) * p.Lmax + row;
+            p.pmax[o] = m; p.psum[o] = l; p.parg[o] = arg;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// lo = x - trunc_tf32(x): the part of x the tensor core drops when it reads x as tf32
+__global__ void tf32_residual_kernel(const float4 *__restrict__ x, float4 *__restrict__ lo, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 r;
+        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo[i] = r;
+    }
+}
+
+// merge the column splits: conf = 1 / sum_j exp(s_j - max) (the soft-max value at the arg-max), idx = arg-max
+__global__ void coarse_merge_kernel(CoarseStatParams p, float *conf01, int64_t *idx01, float *conf10, int64_t *idx10) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int dir = blockIdx.y;
+    const int Lr = p.L[dir];
+    if (i >= (size_t)p.B * Lr) return;
+    const int b = (int)(i / Lr), row = (int)(i % Lr);
+    float m = -INFINITY;
+    int arg = 0;
+    for (int s = 0; s < p.nsplit; ++s) {
+        const size_t o = ((size_t)(dir * p.nsplit + s) * p.B + b) * p.Lmax + row;
+        if (p.pmax[o] > m) { m = p.pmax[o]; arg = p.parg[o]; }
+    }
+    float l = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) {
+        const size_t o = ((size_t)(dir * p.nsplit + s) * p.B + b) * p.Lmax + row;
+        if (p.pmax[o] > -INFINITY) l += p.psum[o] * exp2f(p.pmax[o] - m);
+    }
+    (dir ? conf10 : conf01)[i] = 1.0f / l;
+    (dir ? idx10 : idx01)[i] = arg;
+}
+
+int make_map3(CUtensorMap *tm, const float *base, int B, int L, int C, int rows) {
+    EncodeTiledFn enc = encode_tiled();
+    CASMTR_REQUIRE(enc != nullptr, CASMTR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)L * C * 4};
+    const cuuint32_t box[3] = {BK, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CASMTR_REQUIRE(r == CUDA_SUCCESS, CASMTR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CASMTR_OK;
+}
+
+int pick_nsplit(int B, int L0, int L1) {
+    const int rb = ((L0 > L1 ? L0 : L1) + BM - 1) / BM;
+    const int nt = ((L0 < L1 ? L0 : L1) + BN - 1) / BN;
+    int ns = (4 * 148 + 2 * B * rb - 1) / (2 * B * rb);          // about four waves of CTAs
+    if (ns > nt) ns = nt;
+    return ns < 1 ? 1 : ns;
+}
+
+}  // namespace
+
+size_t coarse_match_workspace(int B, int L0, int L1, int C) {
+    Workspace ws(nullptr, 0);
+    const int Lmax = L0 > L1 ? L0 : L1, ns = pick_nsplit(B, L0, L1);
+    ws.take<float>((size_t)B * L0 * C);
+    ws.take<float>((size_t)B * L1 * C);
+    ws.take<float>((size_t)2 * ns * B * Lmax);
+    ws.take<float>((size_t)2 * ns * B * Lmax);
+    ws.take<int>((size_t)2 * ns * B * Lmax);
+    return ws.off;
+}
+
+int launch_coarse_match(const float *feat0, const float *feat1, float temperature, float *conf01, int64_t *idx01, float *conf10,
+                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    CASMTR_REQUIRE(C % BK == 0 && C >= BK, CASMTR_E_UNSUPPORTED, "coarse_match: C=%d must be a multiple of %d", C, BK);
+    CASMTR_REQUIRE((((uintptr_t)feat0 | (uintptr_t)feat1) & 15) == 0, CASMTR_E_INVALID, "coarse_match: features must be 16-byte aligned");
+    Workspace ws(workspace, workspace_bytes);
+    const int Lmax = L0 > L1 ? L0 : L1, ns = pick_nsplit(B, L0, L1);
+    float *lo0 = ws.take<float>((size_t)B * L0 * C), *lo1 = ws.take<float>((size_t)B * L1 * C);
+    CoarseStatParams p;
+    p.pmax = ws.take<float>((size_t)2 * ns * B * Lmax);
+    p.psum = ws.take<float>((size_t)2 * ns * B * Lmax);
+    p.parg = ws.take<int>((size_t)2 * ns * B * Lmax);
+    CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "coarse_match: workspace %zu < %zu bytes", workspace_bytes, ws.off);
+    p.B = B; p.L[0] = L0; p.L[1] = L1; p.C = C; p.nsplit = ns; p.Lmax = Lmax;
+    p.scale_log2 = LOG2E_F / ((float)C * temperature);
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        tf32_residual_kernel<<<148 * 8, 256, 0, stream>>>((const float4 *)feat0, (float4 *)lo0, (size_t)B * L0 * C / 4);
+    }
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        tf32_residual_kernel<<<148 * 8, 256, 0, stream>>>((const float4 *)feat1, (float4 *)lo1, (size_t)B * L1 * C / 4);
+    }
+    CASMTR_CHECK_LAUNCH("tf32_residual_kernel");
+    CoarseMaps maps;
+    const float *hi[2] = {feat0, feat1}, *lo[2] = {lo0, lo1};
+    const int Ls[2] = {L0, L1};
+    int rc = CASMTR_OK;
+    for (int d = 0; d < 2 && rc == CASMTR_OK; ++d) {
+        rc = make_map3(&maps.a_hi[d], hi[d], B, Ls[d], C, BM);
+        if (rc == CASMTR_OK) rc = make_map3(&maps.a_lo[d], lo[d], B, Ls[d], C, BM);
+        if (rc == CASMTR_OK) rc = make_map3(&maps.b_hi[d], hi[1 - d], B, Ls[1 - d], C, BN);
+        if (rc == CASMTR_OK) rc = make_map3(&maps.b_lo[d], lo[1 - d], B, Ls[1 - d], C, BN);
+    }
+    if (rc != CASMTR_OK) return rc;
+    const size_t smem = 1024 + SM_TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(coarse_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        attr_set = true;
+    }
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        coarse_rowstats_kernel<<<dim3((Lmax + BM - 1) / BM, ns, 2 * B), 192, smem, stream>>>(maps, p);
+        CASMTR_CHECK_LAUNCH("coarse_rowstats_kernel");
+    }
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        coarse_merge_kernel<<<dim3(((size_t)B * Lmax + 255) / 256, 2), 256, 0, stream>>>(p, conf01, idx01, conf10, idx10);
+        CASMTR_CHECK_LAUNCH("coarse_merge_kernel");
+    }
+    return CASMTR_OK;
+}

@@ -92,6 +92,11 @@ size_t match_tile_smem_bytes();
 bool match_tile_applicable(const MatchParams &p);
 int launch_cascade_match_tile(const MatchParams &p, cudaStream_t stream);
 
+// ---- coarse_match.cu: dense dual-softmax row / column statistics on tcgen05
+size_t coarse_match_workspace(int B, int L0, int L1, int C);
+int launch_coarse_match(const float *feat0, const float *feat1, float temperature, float *conf01, int64_t *idx01, float *conf10,
+                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
 // ---- extract.cu
 int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01, const int64_t *next_idx01,
                          const int64_t *next_idx10, uint8_t *mask_out, int64_t *b_ids, int64_t *i_ids,

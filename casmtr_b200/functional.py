@@ -220,6 +220,24 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
     return o
 
 
+def coarse_match_forward(feat0, feat1, temperature=0.1):
+    """Dense dual-softmax statistics (tcgen05): feat0 [B,L0,C], feat1 [B,L1,C] -> dict next_conf01 [B,L0], next_idx01 [B,L0]
+    (int64), next_conf10 [B,L1], next_idx10 [B,L1]; the L0 x L1 similarity matrix is never materialised."""
+    _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
+    B, L0, Cc = feat0.shape
+    L1 = feat1.shape[1]
+    dev = feat0.device
+    o = {'next_conf01': torch.empty(B, L0, dtype=torch.float32, device=dev), 'next_idx01': torch.empty(B, L0, dtype=torch.int64, device=dev),
+         'next_conf10': torch.empty(B, L1, dtype=torch.float32, device=dev), 'next_idx10': torch.empty(B, L1, dtype=torch.int64, device=dev)}
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_coarse_match_workspace_bytes(B, L0, L1, Cc)
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_coarse_match_fwd(_ptr(feat0), _ptr(feat1), float(temperature), _ptr(o['next_conf01']), _ptr(o['next_idx01']),
+                                            _ptr(o['next_conf10']), _ptr(o['next_idx10']), B, L0, L1, Cc, _ptr(ws), ws.numel(),
+                                            _stream(feat0)), 'casmtr_coarse_match_fwd')
+    return o
+
+
 def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_thr, border_rm, nms_window=None,
                   pre_confs=(), pre_thrs=(), double_check=True, pad_mask0=None, pad_mask1=None,
                   scale0=None, scale1=None, defer=False):

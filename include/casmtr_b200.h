@@ -76,7 +76,8 @@ enum {
     CASMTR_K_FINE_MATCH = 7,
     CASMTR_K_OPS = 8,           /* op-level drop-ins (score5d / value_agg / score3d) */
     CASMTR_K_CASCADE_FALLBACK = 9, /* gather kernel over the cells the TMA-tiled cascade kernels could not serve */
-    CASMTR_K_COUNT = 10
+    CASMTR_K_COARSE_MATCH = 10, /* dense dual-softmax statistics on tcgen05 (SURVEY section 8f "next" #1) */
+    CASMTR_K_COUNT = 11
 };
 /* Total number of kernels this library has launched in this process (all threads). */
 CASMTR_API uint64_t casmtr_launch_count(void);
@@ -178,6 +179,16 @@ CASMTR_API int casmtr_cascade_match_fwd(const float *feat0, const float *feat1,
                              float *conf10, float *next_conf10, int64_t *next_idx10,
                              int B, int L0, int L1, int C, int K, int w0, int w1,
                              void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
+/* ---------------------------------------------------------------- dense coarse matching statistics
+ * Reference: src/model/functions/coarse_matching.py:60-75.  feat0 [B,L0,C], feat1 [B,L1,C] fp32 (un-normalised; the
+ * 1/sqrt(C) of :61 is applied inside), sim = <f0,f1> / (C * temperature).  Outputs, without ever forming the L0 x L1 matrix:
+ *   next_conf01 [B,L0] = max_j softmax_j(sim)[i,:],  next_idx01 [B,L0] = argmax_j;  next_conf10 / next_idx10 [B,L1] likewise
+ *   over i.  GEMM on tcgen05 (kind::tf32, 3-term split for fp32 accuracy), softmax statistics in the epilogue.  C % 32 == 0. */
+CASMTR_API size_t casmtr_coarse_match_workspace_bytes(int B, int L0, int L1, int C);
+CASMTR_API int casmtr_coarse_match_fwd(const float *feat0, const float *feat1, float temperature,
+                            float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                            int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS + match extraction (R7) */
 
