@@ -1,0 +1,42 @@
+"""Drop-in for the inference statistics of the reference's dense coarse matcher (src/model/functions/coarse_matching.py:22-89,
+SURVEY.md section 8f "next" #1).  The reference forms sim [B,L,S], two soft-maxes and their product (four 468 MB tensors at
+832x832); the cascade stages only consume next_idx_c01/c10 and next_conf_c01/c10, which libcasmtr_b200 computes on the
+tensor cores without materialising the matrix (casmtr_coarse_match_fwd).
+
+What is NOT produced: `conf_matrix` and the mutual-nearest-neighbour match list of get_coarse_match (:91-153).  In the cascade
+models they feed the training supervision only (the final matches come from the last cascade stage); they are set to None.
+Masks (padded images) are not supported by the fused kernel yet and raise."""
+import torch.nn as nn
+
+from . import functional as F
+
+
+class CoarseMatching(nn.Module):
+    def __init__(self, config, coarse_config=None):
+        super().__init__()
+        self.config = config
+        self.thr = config['thr']
+        self.border_rm = config['border_rm']
+        self.train_coarse_percent = config['train_coarse_percent']
+        self.train_pad_num_gt_min = config['train_pad_num_gt_min']
+        self.next_topk = coarse_config.get('next_topk', None) if coarse_config is not None else None
+        self.match_type = config['match_type']
+        self.temperature = config['dsmax_temperature']
+        assert self.match_type == 'dual_softmax'
+
+    def forward(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None, level='8c'):
+        """feat_c0 [N,L,C], feat_c1 [N,S,C] -> data[f'stage_{level}'] with next_idx_c01/c10 [N,L]/[N,S] int64 and
+        next_conf_c01/c10 fp32 (reference :70-84)."""
+        if self.training:
+            raise NotImplementedError('casmtr_b200.CoarseMatching implements the inference statistics only')
+        if mask_c0 is not None or mask_c1 is not None:
+            raise NotImplementedError('casmtr_b200.CoarseMatching: padding masks are not supported by the fused kernel')
+        o = F.coarse_match_forward(feat_c0.float().contiguous(), feat_c1.float().contiguous(), self.temperature)
+        data[f'stage_{level}'] = {
+            'conf_matrix': None, 'next_conf_c01_topk': None, 'next_idx_c01_topk': None,
+            'next_conf_c10_topk': None, 'next_idx_c10_topk': None,
+            'next_idx_c01': o['next_idx01'], 'next_idx_c10': o['next_idx10'],
+            'next_conf_c01': o['next_conf01'], 'next_conf_c10': o['next_conf10'],
+            'next_conf_c01_s': None, 'next_idx_c01_s': None,
+            'b_ids': None, 'i_ids': None, 'j_ids': None, 'gt_mask': None, 'm_bids': None,
+            'mkpts0_c': None, 'mkpts1_c': None, 'mconf': None}

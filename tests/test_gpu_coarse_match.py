@@ -36,3 +36,18 @@ def test_coarse_match_stats(dev, B, L0, L1, C):
     assert torch.equal(o['next_idx01'].cpu()[clear01], i01[clear01])
     assert torch.equal(o['next_idx10'].cpu()[clear10], i10[clear10])
     assert clear01.float().mean() > 0.99
+
+
+def test_coarse_matching_module(dev):
+    import casmtr_b200
+    cfg = {'thr': 0.2, 'border_rm': 0, 'match_type': 'dual_softmax', 'dsmax_temperature': 0.1, 'train_coarse_percent': 0.3,
+           'train_pad_num_gt_min': 200}
+    g = torch.Generator().manual_seed(5)
+    f0 = torch.randn(1, 400, 256, generator=g)
+    f1 = 0.8 * f0[:, torch.randperm(400, generator=g)] + 0.6 * torch.randn(1, 400, 256, generator=g)
+    data = {}
+    casmtr_b200.CoarseMatching(cfg).eval()(f0.to(dev), f1.to(dev), data, level='8c')
+    c01, i01, c10, i10, g01, g10 = _ref(f0, f1, 0.1)
+    st = data['stage_8c']
+    assert torch.equal(st['next_idx_c01'].cpu()[g01 > 1e-4], i01[g01 > 1e-4]) and (st['next_conf_c10'].cpu() - c10).abs().max() < 1e-3
+    assert st['conf_matrix'] is None
