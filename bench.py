@@ -377,6 +377,35 @@ def run_ours(args):
                   'gbps': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6, 1),
                   'frac_of_hbm_peak': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6 / peak, 4)}
 
+    # ---- SURVEY section 8f "next" #1, reported beside the hot path (not part of `value`): dense coarse matching statistics
+    # of one pair at the 1/8 grid on the tensor cores
+    next_rows = None
+    if rank == 0:
+        try:
+            g = torch.Generator().manual_seed(7)
+            L8 = wl.h8 * wl.w8
+            cf0 = torch.randn(wl.B, L8, wl.C8, generator=g).to(dev)
+            cf1 = (0.8 * cf0.cpu()[:, torch.randperm(L8, generator=g)] + 0.6 * torch.randn(wl.B, L8, wl.C8, generator=g)).to(dev)
+            for _ in range(3):
+                F.coarse_match_forward(cf0, cf1, 0.1)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                F.coarse_match_forward(cf0, cf1, 0.1)
+            c1.record()
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1) / 10
+            alg = 2 * 2.0 * wl.B * L8 * L8 * wl.C8                      # both directions, fp32-equivalent FLOPs
+            tpeak = tensor_peak()
+            next_rows = {'coarse_matching': {
+                'ms_per_call': cms, 'alg_tflops': alg / cms / 1e9, 'issued_tf32_tflops': 3 * alg / cms / 1e9,
+                'roofline': {'bound': 'tensor', 'achieved': alg / cms / 1e9, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': alg / cms / 1e9 / tpeak,
+                             'note': 'fp32-accurate path = 3 TF32 MMAs per product at half the bf16 rate: ceiling = peak / 6'},
+                'what': 'CoarseMatching next_idx/next_conf (both directions) at the 1/8 grid, tcgen05 kind::tf32 3-term split'}}
+            del cf0, cf1
+        except Exception as e:      # noqa: BLE001
+            next_rows = {'coarse_matching': {'error': str(e)[:300]}}
     host_ms = None
     if True:        # host-side cost of enqueueing one step (no device wait): how launch-bound the path is
         torch.cuda.synchronize()
@@ -394,7 +423,7 @@ def run_ours(args):
         'data': 'synthetic', 'config': config_dict(wl, n_gpus), 'e2e': e2e, 'gpu_launches': int(launches) * args.steps,
         'gpu_launches_per_step': int(launches), 'clocks': clocks, 'roofline': roofline, 'qtatt_call_roofline': qtatt_call,
         'execution': mode, 'ms_per_step_eager_instrumented': ms_eager, 'value_eager_instrumented': wl.B * n_gpus / (ms_eager / 1000.0),
-        'cuda_graph': graph_info, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
+        'cuda_graph': graph_info, 'next_rows': next_rows, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         try:        # the same algorithm as plain torch CUDA ops on this GPU (extra context, not part of the contract)
@@ -419,6 +448,14 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def tensor_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['bf16_tflops'])
+    return 1590.0
 
 
 def ncu_stats():

@@ -248,12 +248,20 @@ int make_map3(CUtensorMap *tm, const float *base, int B, int L, int C, int rows)
     return CASMTR_OK;
 }
 
+// column splits per row block: enough CTAs for a few waves of the (one CTA per SM) grid, with the fullest last wave
 int pick_nsplit(int B, int L0, int L1) {
-    const int rb = ((L0 > L1 ? L0 : L1) + BM - 1) / BM;
+    const int rb = ((L0 + BM - 1) / BM + (L1 + BM - 1) / BM) * B;        // row blocks of both directions
     const int nt = ((L0 < L1 ? L0 : L1) + BN - 1) / BN;
-    int ns = (4 * 148 + 2 * B * rb - 1) / (2 * B * rb);          // about four waves of CTAs
-    if (ns > nt) ns = nt;
-    return ns < 1 ? 1 : ns;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ns = 1; ns <= nt && ns <= 16; ++ns) {
+        const long long ctas = (long long)rb * ns, waves = (ctas + 147) / 148;
+        if (waves > 12) break;
+        const double eff = (double)ctas / (double)(waves * 148);
+        if (ctas >= 2 * 148 && eff > best_eff + 0.02) { best_eff = eff; best = ns; }
+        else if (ctas < 2 * 148) best = ns;                              // keep splitting until the machine is covered twice
+    }
+    return best;
 }
 
 }  // namespace
