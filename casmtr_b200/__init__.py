@@ -7,7 +7,7 @@ mirror the reference's module API.
 from .modules.quadtree_attention import QTAttA, QTAttB, QTAttGuided, CascadeQTAttB  # noqa: F401
 from .functions.quadtree_attention import score_computation_op, value_aggregation_op  # noqa: F401
 from .cascade_matching import CascadeMatching, PostProcess, ScoreComputation  # noqa: F401
-from .fine_matching import CascadeFineMatching, FineMatching  # noqa: F401
+from .fine_matching import CascadeFineMatching, CascadeFinePreprocess, FineMatching  # noqa: F401
 from .coarse_matching import CoarseMatching  # noqa: F401
 
 __version__ = '0.1.0'

@@ -398,6 +398,14 @@ int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_
     return launch_pack_matches(b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, M, pair_offset, out, (cudaStream_t)stream);
 }
 
+int casmtr_fine_window_gather(const float *feat, const int64_t *b_ids, const int64_t *ids, float *out, int M, int C, int Hf, int Wf,
+                              int wc, int stride, int W, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(M >= 0 && C > 0 && Hf > 0 && Wf > 0 && wc > 0 && stride > 0 && W > 0 && (W & 1), CASMTR_E_INVALID,
+                   "fine_window_gather: bad sizes");
+    CASMTR_REQUIRE(M == 0 || (feat && b_ids && ids && out), CASMTR_E_INVALID, "fine_window_gather: null pointer");
+    return launch_fine_window_gather(feat, b_ids, ids, out, M, C, Hf, Wf, wc, stride, W, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ fine matching
 int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
                           const float *scale1_b, const int64_t *b_ids, float scale,

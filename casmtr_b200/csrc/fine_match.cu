@@ -49,7 +49,43 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const float *__restrict
     }
 }
 
+// Window gather of CascadeFinePreprocess (src/model/functions/fine_matching.py:47-55): the reference unfolds the WHOLE fine
+// map (F.unfold, 277 MB - 1.1 GB) and then selects M rows; this reads only the M windows.  CTA = one match: W*W pixels x C
+// channels of the NCHW fine map -> out[m, W*W, C] (channel innermost), zero padding outside the map, via a smem transpose.
+__global__ void __launch_bounds__(256) fine_window_gather_kernel(const float *__restrict__ feat, const int64_t *__restrict__ b_ids,
+                                                                  const int64_t *__restrict__ ids, float *__restrict__ out,
+                                                                  int C, int Hf, int Wf, int wc, int stride, int W) {
+    extern __shared__ float tile[];                 // [W*W][C + 1]
+    const int m = blockIdx.x, WW = W * W, ld = C + 1;
+    const long long b = b_ids[m], id = ids[m];
+    const int cy = (int)(id / wc) * stride - W / 2, cx = (int)(id % wc) * stride - W / 2;      // top-left fine pixel of the window
+    const float *fb = feat + (size_t)b * C * Hf * Wf;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {                                    // one window row of one channel per thread
+        const int c = i / W, wy = i - c * W;
+        const int y = cy + wy;
+        const float *src = fb + ((size_t)c * Hf + y) * Wf;
+        for (int wx = 0; wx < W; ++wx) {
+            const int x = cx + wx;
+            tile[(wy * W + wx) * ld + c] = (y >= 0 && y < Hf && x >= 0 && x < Wf) ? __ldg(src + x) : 0.f;
+        }
+    }
+    __syncthreads();
+    float *o = out + (size_t)m * WW * C;
+    for (int i = threadIdx.x; i < WW * C; i += blockDim.x) o[i] = tile[(i / C) * ld + (i % C)];
+}
+
 }  // namespace
+
+int launch_fine_window_gather(const float *feat, const int64_t *b_ids, const int64_t *ids, float *out, int M, int C, int Hf, int Wf,
+                              int wc, int stride, int W, cudaStream_t stream) {
+    if (M == 0) return CASMTR_OK;
+    const size_t smem = sizeof(float) * (size_t)W * W * (C + 1);
+    CASMTR_REQUIRE(smem <= 48 * 1024, CASMTR_E_UNSUPPORTED, "fine_window_gather: window %d x C=%d exceeds shared memory", W, C);
+    LaunchScope ls(CASMTR_K_FINE_MATCH, stream);
+    fine_window_gather_kernel<<<M, 256, smem, stream>>>(feat, b_ids, ids, out, C, Hf, Wf, wc, stride, W);
+    CASMTR_CHECK_LAUNCH("fine_window_gather_kernel");
+    return CASMTR_OK;
+}
 
 int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, const float *scale1_b,
                       const int64_t *b_ids, float scale, float *expec_f, float *mkpts1_f,

@@ -316,6 +316,19 @@ def pack_matches(m, pair_offset, cap):
     return out
 
 
+def fine_window_gather(feat, b_ids, ids, wc, stride, W=5):
+    """feat [B,C,Hf,Wf] fp32, b_ids / ids [M] int64 (ids on a coarse grid of width wc, fine = coarse * stride)
+    -> windows [M, W*W, C]: F.unfold(feat, W, stride, padding=W//2) selected at (b_ids, ids), without the unfold."""
+    _chk(feat, 'feat', torch.float32), _chk(b_ids, 'b_ids', torch.int64), _chk(ids, 'ids', torch.int64)
+    B, Cc, Hf, Wf = feat.shape
+    M = b_ids.shape[0]
+    out = torch.empty(M, W * W, Cc, dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(lib().casmtr_fine_window_gather(_ptr(feat), _ptr(b_ids), _ptr(ids), _ptr(out), M, Cc, Hf, Wf, int(wc), int(stride), int(W),
+                                              _stream(feat)), 'casmtr_fine_window_gather')
+    return out
+
+
 def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None):
     """-> (expec_f [M,3], mkpts1_f [M,2])."""
     _chk(feat_f0, 'feat_f0', torch.float32), _chk(feat_f1, 'feat_f1', torch.float32)

@@ -230,6 +230,13 @@ CASMTR_API int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, c
                         const float *mkpts0, const float *mkpts1, int M, int64_t pair_offset, int capacity,
                         unsigned char *out, casmtr_stream_t stream);
 
+/* Window gather of CascadeFinePreprocess (src/model/functions/fine_matching.py:47-55; SURVEY 8f "next" #4): for match m the
+ * W x W window of the fine map feat [B,C,Hf,Wf] centred on coarse token ids[m] (grid width wc, fine = coarse * stride),
+ * zero padded, written as out [M, W*W, C].  Equals F.unfold(feat, W, stride=stride, padding=W/2)[b_ids, ids] of the reference
+ * without unfolding the whole map. */
+CASMTR_API int casmtr_fine_window_gather(const float *feat, const int64_t *b_ids, const int64_t *ids, float *out,
+                              int M, int C, int Hf, int Wf, int wc, int stride, int W, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- fine matching (R8) */
 
 /* feat_f0/feat_f1 [M,WW,C]; mkpts1_c [M,2]; scale = hw0_i[0]/hw0_f[0]; scale1_b NULL or [B,2] with

@@ -143,3 +143,30 @@ def test_pack_matches_kernel(dev):
     assert torch.equal(back['b_ids'], m['b_ids'] + 5) and torch.equal(back['mkpts1'], m['mkpts1'])
     empty = F.pack_matches({k: v[:0].to(dev) for k, v in m.items()}, pair_offset=0, cap=4).cpu()
     assert int(empty[0, :8].clone().view(torch.int64)) == 0
+
+
+@pytest.mark.parametrize('cat', [False, True])
+def test_fine_preprocess_vs_unfold(dev, cat):
+    """CascadeFinePreprocess: gathered windows == the reference formulation F.unfold(...)[b_ids, ids] (fine_matching.py:47-55)."""
+    import torch.nn.functional as tF
+    B, C, Hc, Wc, stride, W = 2, 64, 24, 40, 2, 5
+    g = torch.Generator().manual_seed(8)
+    ff0, ff1 = torch.randn(B, C, Hc * stride, Wc * stride, generator=g), torch.randn(B, C, Hc * stride, Wc * stride, generator=g)
+    fc0, fc1 = torch.randn(B, Hc * Wc, 128, generator=g), torch.randn(B, Hc * Wc, 128, generator=g)
+    M = 300
+    b = torch.randint(0, B, (M,), generator=g).sort()[0]
+    i, j = torch.randint(0, Hc * Wc, (M,), generator=g), torch.randint(0, Hc * Wc, (M,), generator=g)
+    i[:4] = torch.tensor([0, Wc - 1, (Hc - 1) * Wc, Hc * Wc - 1])                  # corners: zero padding
+    mod = casmtr_b200.CascadeFinePreprocess({'fine_concat_coarse_feat': cat, 'fine_window_size': W}, {'d_model': C}, {'d_model': 128}, '4c').eval()
+    data = {'hw0_f': (Hc * stride, Wc * stride), 'hw0_4c': (Hc, Wc), 'hw1_4c': (Hc, Wc), 'stage_4c': {'b_ids': b.to(dev), 'i_ids': i.to(dev), 'j_ids': j.to(dev)}}
+    with torch.no_grad():
+        o0, o1 = mod.to(dev)(ff0.to(dev), ff1.to(dev), fc0.to(dev), fc1.to(dev), data)
+        u0 = tF.unfold(ff0, (W, W), stride=stride, padding=W // 2).reshape(B, C, W * W, -1).permute(0, 3, 2, 1)[b, i]
+        u1 = tF.unfold(ff1, (W, W), stride=stride, padding=W // 2).reshape(B, C, W * W, -1).permute(0, 3, 2, 1)[b, j]
+        if cat:
+            m = mod.cpu()
+            cw = m.down_proj(torch.cat([fc0[b, i], fc1[b, j]], 0))
+            cf = m.merge_feat(torch.cat([torch.cat([u0, u1], 0), cw.unsqueeze(1).expand(-1, W * W, -1)], -1))
+            u0, u1 = torch.chunk(cf, 2, dim=0)
+    tol = 1e-3 if cat else 0.0                      # the gather is exact; the Linear layers run in cuBLAS (TF32 off) vs CPU
+    assert (o0.cpu() - u0).abs().max() <= tol and (o1.cpu() - u1).abs().max() <= tol
