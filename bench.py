@@ -406,6 +406,40 @@ def run_ours(args):
             del cf0, cf1
         except Exception as e:      # noqa: BLE001
             next_rows = {'coarse_matching': {'error': str(e)[:300]}}
+    if rank == 0:   # "next" #2 / #4: token-major QTAtt entry (pyramid inside) and the fine-window gather, timed alone
+        def _time(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(n):
+                fn()
+            c1.record()
+            torch.cuda.synchronize()
+            return c0.elapsed_time(c1) / n
+        try:
+            call = dev_in['qt'][0]
+            tok = [t[0].flatten(2).transpose(1, 2).contiguous() for t in (call['q'], call['k'], call['v'])]
+            t_tok = _time(lambda: F.qtatt_tokens_forward(tok[0], tok[1], tok[2], (wl.h8, wl.w8), (wl.h8, wl.w8), wl.topks, wl.nh8, weight=call['weight']))
+            t_pyr = _time(lambda: F.qtatt_forward(call['q'], call['k'], call['v'], wl.topks, wl.nh8, weight=call['weight']))
+            next_rows['quadtree_attention_tokens'] = {
+                'ms_per_call_tokens_entry': t_tok, 'ms_per_call_nchw_pyramid_entry': t_pyr,
+                'what': 'QTAttB at 1/8 from token-major level-0 q/k/v with the avg-pool pyramid built inside (casmtr_qtatt_tokens_fwd) '
+                        'vs the NCHW pyramid lists of the reference API (casmtr_qtatt_fwd); the reference additionally pays 6 avg_pool2d launches upstream'}
+            del tok
+            M = max(n_matches, 1)
+            g = torch.Generator().manual_seed(9)
+            ff = torch.randn(wl.B, 64, wl.hf, wl.wf, generator=g).to(dev)
+            bi = torch.zeros(M, dtype=torch.int64, device=dev)
+            ii = torch.randint(0, wl.h4 * wl.w4, (M,), generator=g).to(dev)
+            t_g = _time(lambda: F.fine_window_gather(ff, bi, ii, wl.w4, wl.hf // wl.h4, 5))
+            t_u = _time(lambda: torch.nn.functional.unfold(ff, (5, 5), stride=wl.hf // wl.h4, padding=2).reshape(wl.B, 64, 25, -1).permute(0, 3, 2, 1)[bi, ii], n=5)
+            next_rows['fine_preprocess'] = {'ms_per_map_gather': t_g, 'ms_per_map_unfold_select_torch': t_u, 'matches': M,
+                                            'what': 'CascadeFinePreprocess window crop of one fine map: gather kernel vs the reference formulation (F.unfold + select) on the same GPU'}
+            del ff
+        except Exception as e:      # noqa: BLE001
+            next_rows['next_rows_error'] = str(e)[:300]
     host_ms = None
     if True:        # host-side cost of enqueueing one step (no device wait): how launch-bound the path is
         torch.cuda.synchronize()

@@ -49,6 +49,11 @@ SIGNATURES = {
     'casmtr_qtatt_fwd': (C.c_int, [C.POINTER(QtattDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    c_float_p, c_float_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_qtatt_tokens_fwd': (C.c_int, [C.POINTER(QtattDesc), c_float_p, c_float_p, c_float_p,
+                                          c_float_p, c_float_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_cascade_qtatt_tokens_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
+                                        + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_cascade_qtatt_workspace_bytes': (C.c_size_t, [C.c_int] * 6),
     'casmtr_cascade_qtatt_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                  + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),

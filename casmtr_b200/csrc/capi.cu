@@ -182,6 +182,10 @@ size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc) {
     return ws.off;
 }
 
+// the levels themselves, on token-major pyramids bf.q/k/v
+static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream);
+
 int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
                      const float *const *queries, const float *const *keys, const float *const *values,
                      const float *level_weight, float *out,
@@ -208,7 +212,42 @@ int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
     }
     rc = launch_transpose_jobs(jobs, d->B, stream);
     if (rc != CASMTR_OK) return rc;
+    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
+}
 
+int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const float *k0, const float *v0,
+                            const float *level_weight, float *out,
+                            int64_t *const *topk_idx_out, float *const *topk_score_out,
+                            void *workspace, size_t workspace_bytes, casmtr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_qtatt_desc(d);
+    if (rc != CASMTR_OK) return rc;
+    CASMTR_REQUIRE(q0 && k0 && v0 && out && workspace, CASMTR_E_INVALID, "qtatt_tokens: null pointer");
+    CASMTR_REQUIRE(d->type == 1 || level_weight != nullptr, CASMTR_E_INVALID, "qtatt_tokens: QTAttB needs the level weight vector");
+    for (int l = 1; l < d->levels; ++l)
+        CASMTR_REQUIRE(d->qh[l] == d->qh[l - 1] / 2 && d->qw[l] == d->qw[l - 1] / 2 && d->kh[l] == d->kh[l - 1] / 2 && d->kw[l] == d->kw[l - 1] / 2,
+                       CASMTR_E_INVALID, "qtatt_tokens: level %d is not the 2x2 pooling of level %d", l, l - 1);
+    Workspace ws(workspace, workspace_bytes);
+    QtattBuffers bf;
+    carve_qtatt(d, ws, bf);
+    CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "qtatt_tokens: workspace %zu < %zu bytes", workspace_bytes, ws.off);
+    const int C = d->nhead * d->D;
+    bf.q[0] = const_cast<float *>(q0); bf.k[0] = const_cast<float *>(k0); bf.v[0] = const_cast<float *>(v0);   // read in place
+    for (int l = 1; l < d->levels; ++l) {
+        PoolJobs pj;
+        pj.n = 3;
+        pj.job[0] = PoolJob{bf.q[l - 1], bf.q[l], d->qh[l - 1], d->qw[l - 1]};
+        pj.job[1] = PoolJob{bf.k[l - 1], bf.k[l], d->kh[l - 1], d->kw[l - 1]};
+        pj.job[2] = PoolJob{bf.v[l - 1], bf.v[l], d->kh[l - 1], d->kw[l - 1]};
+        rc = launch_pool_tokens(pj, d->B, C, stream);
+        if (rc != CASMTR_OK) return rc;
+    }
+    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
+}
+
+static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream) {
+    int rc = CASMTR_OK;
     const float *wts = d->type == 0 ? level_weight : nullptr;
     for (int i = 0; i < d->levels; ++i) {
         const int l = d->levels - 1 - i;
@@ -259,12 +298,33 @@ size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1
     return ws.off;
 }
 
+static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
+                              const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
+                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
                              const int64_t *topk_pos, const float *rel_pos,
                              float *message, int64_t *upsampled_idx,
                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
-                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    return cascade_qtatt_impl(false, query, key, value, topk_pos, rel_pos, message, upsampled_idx, B, nhead, D, h0, w0, h1, w1, k, dilated,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int casmtr_cascade_qtatt_tokens_fwd(const float *query, const float *key, const float *value,
+                                    const int64_t *topk_pos, const float *rel_pos,
+                                    float *message, int64_t *upsampled_idx,
+                                    int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                                    void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    return cascade_qtatt_impl(true, query, key, value, topk_pos, rel_pos, message, upsampled_idx, B, nhead, D, h0, w0, h1, w1, k, dilated,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
+                              const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
+                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     CASMTR_REQUIRE(D == 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: head dim %d unsupported (D == 32)", D);
     CASMTR_REQUIRE(B >= 1 && nhead >= 1 && h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0, CASMTR_E_INVALID, "cascade_qtatt: bad sizes");
     CASMTR_REQUIRE(h0 % 2 == 0 && w0 % 2 == 0, CASMTR_E_INVALID, "cascade_qtatt: query grid %dx%d must be even", h0, w0);
@@ -273,18 +333,25 @@ int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *
     CASMTR_REQUIRE(query && key && value && topk_pos && message && workspace, CASMTR_E_INVALID, "cascade_qtatt: null pointer");
     const int C = nhead * D;
     Workspace ws(workspace, workspace_bytes);
-    float *qt = ws.take<float>((size_t)B * h0 * w0 * C);
-    float *kt = ws.take<float>((size_t)B * h1 * w1 * C);
-    float *vt = ws.take<float>((size_t)B * h1 * w1 * C);
+    const float *qt = query, *kt = key, *vt = value;
+    if (!token_major) {
+        float *q_ = ws.take<float>((size_t)B * h0 * w0 * C);
+        float *k_ = ws.take<float>((size_t)B * h1 * w1 * C);
+        float *v_ = ws.take<float>((size_t)B * h1 * w1 * C);
+        qt = q_; kt = k_; vt = v_;
+    }
     int *fb = ws.take<int>((size_t)B * (h0 / 2) * (w0 / 2) + 1);
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "cascade_qtatt: workspace %zu < %zu bytes", workspace_bytes, ws.off);
-    TransposeJobs jobs;
-    jobs.n = 3;
-    jobs.job[0] = TransposeJob{query, qt, C, h0 * w0, 0};
-    jobs.job[1] = TransposeJob{key, kt, C, h1 * w1, 0};
-    jobs.job[2] = TransposeJob{value, vt, C, h1 * w1, 0};
-    int rc = launch_transpose_jobs(jobs, B, stream);
-    if (rc != CASMTR_OK) return rc;
+    int rc = CASMTR_OK;
+    if (!token_major) {
+        TransposeJobs jobs;
+        jobs.n = 3;
+        jobs.job[0] = TransposeJob{query, const_cast<float *>(qt), C, h0 * w0, 0};
+        jobs.job[1] = TransposeJob{key, const_cast<float *>(kt), C, h1 * w1, 0};
+        jobs.job[2] = TransposeJob{value, const_cast<float *>(vt), C, h1 * w1, 0};
+        rc = launch_transpose_jobs(jobs, B, stream);
+        if (rc != CASMTR_OK) return rc;
+    }
     FineParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.q = qt; fp.k = kt; fp.v = vt;

@@ -14,6 +14,16 @@ struct TransposeJobs {
     int n;
 };
 int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream);
+struct PoolJob {
+    const float *src;   // [B, h*w, C] token-major
+    float *dst;         // [B, (h/2)*(w/2), C]
+    int h, w;
+};
+struct PoolJobs {
+    PoolJob job[3];
+    int n;
+};
+int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream);
 int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
                        size_t n_tok, int nh, int k, cudaStream_t stream);
 

@@ -5,6 +5,8 @@
 // here all (up to 12) maps of one attention call go through ONE batched tile-transpose launch.
 // Token-major makes one (token, head) row exactly one 128-byte line, which is what the gather
 // kernels want.  HBM-bound: 4 B read + 4 B written per element.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -105,6 +107,45 @@ int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
     LaunchScope ls(CASMTR_K_LAYOUT, stream);
     transpose_jobs_kernel<<<dim3(total, B), 256, 0, stream>>>(jobs);
     CASMTR_CHECK_LAUNCH("transpose_jobs_kernel");
+    return CASMTR_OK;
+}
+
+// 2x2 average pooling of token-major maps [B, h*w, C] -> [B, (h/2)*(w/2), C]: one pyramid level of
+// QuadtreeAttention.forward (src/model/modules/quadtree_attention.py:86-89, F.avg_pool2d(kernel 2, stride 2)); the four
+// taps are summed in avg_pool2d's window order.  Thread = 4 channels of one output token; up to 3 maps (q, k, v) per launch.
+__global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4) {
+    const int j = blockIdx.z, b = blockIdx.y;
+    const PoolJob jb = jobs.job[j];
+    const int ho = jb.h >> 1, wo = jb.w >> 1;
+    const size_t n = (size_t)ho * wo * C4;
+    const float4 *src = reinterpret_cast<const float4 *>(jb.src) + (size_t)b * jb.h * jb.w * C4;
+    float4 *dst = reinterpret_cast<float4 *>(jb.dst) + (size_t)b * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int t = (int)(i / C4), y = t / wo, x = t - y * wo;
+        const float4 *p = src + ((size_t)(2 * y) * jb.w + 2 * x) * C4 + c;
+        const float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)jb.w * C4), d = __ldg(p + (size_t)(jb.w + 1) * C4);
+        float4 o;
+        o.x = (((a.x + bb.x) + cc.x) + d.x) * 0.25f;
+        o.y = (((a.y + bb.y) + cc.y) + d.y) * 0.25f;
+        o.z = (((a.z + bb.z) + cc.z) + d.z) * 0.25f;
+        o.w = (((a.w + bb.w) + cc.w) + d.w) * 0.25f;
+        dst[i] = o;
+    }
+}
+
+int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) {
+    if (jobs.n == 0 || B == 0) return CASMTR_OK;
+    CASMTR_REQUIRE(C % 4 == 0, CASMTR_E_UNSUPPORTED, "pool_tokens: C=%d must be a multiple of 4", C);
+    size_t nmax = 0;
+    for (int i = 0; i < jobs.n; ++i) {
+        CASMTR_REQUIRE((((uintptr_t)jobs.job[i].src | (uintptr_t)jobs.job[i].dst) & 15) == 0, CASMTR_E_INVALID, "pool_tokens: unaligned map");
+        nmax = std::max(nmax, (size_t)(jobs.job[i].h / 2) * (jobs.job[i].w / 2) * (C / 4));
+    }
+    if (nmax == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
+    pool_tokens_kernel<<<dim3((unsigned)std::min<size_t>((nmax + 255) / 256, 148 * 8), B, jobs.n), 256, 0, stream>>>(jobs, C / 4);
+    CASMTR_CHECK_LAUNCH("pool_tokens_kernel");
     return CASMTR_OK;
 }
 

@@ -159,12 +159,67 @@ def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B
     return out
 
 
-def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True):
-    """Fused CascadeQTAttB forward -> (message [B,h0*w0,C], upsampled_idx [B,h0*w0,4k] int64 or None)."""
+def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn_type='B', return_topk=False):
+    """QTAttA / QTAttB from the finest level only, token-major: q0 [B, hq*wq, C], k0 / v0 [B, hk*wk, C] fp32; the
+    avg-pool pyramid of len(topks) levels is built inside (casmtr_qtatt_tokens_fwd).  Returns as qtatt_forward."""
+    _chk(q0, 'q0', torch.float32), _chk(k0, 'k0', torch.float32), _chk(v0, 'v0', torch.float32)
+    n = len(topks)
+    if not 1 <= n <= _lib.MAX_LEVELS:
+        raise RuntimeError(f'need 1..{_lib.MAX_LEVELS} pyramid levels, got {n}')
+    B, Lq, Cc = q0.shape
+    (hq, wq), (hk, wk) = hw_q, hw_k
+    if Lq != hq * wq or k0.shape != (B, hk * wk, Cc) or v0.shape != k0.shape:
+        raise RuntimeError(f'token maps {tuple(q0.shape)} / {tuple(k0.shape)} / {tuple(v0.shape)} do not match grids {hw_q} / {hw_k}')
+    if any(s % (1 << (n - 1)) for s in (hq, wq, hk, wk)):
+        raise RuntimeError(f'grids {hw_q} / {hw_k} are not divisible by 2^{n - 1}')
+    dev = q0.device
+    d = QtattDesc()
+    d.B, d.nhead, d.D, d.levels, d.type = B, nhead, Cc // nhead, n, 1 if attn_type == 'A' else 0
+    for l in range(n):
+        d.qh[l], d.qw[l], d.kh[l], d.kw[l], d.topks[l] = hq >> l, wq >> l, hk >> l, wk >> l, int(topks[l])
+    if d.type == 0:
+        if weight is None:
+            raise RuntimeError('QTAttB needs the level weight parameter')
+        weight = _chk(weight.detach().to(torch.float32).contiguous(), 'weight', torch.float32)
+        if weight.numel() < n:
+            raise RuntimeError('weight shorter than the pyramid')
+    out = torch.empty(B, Lq, nhead, Cc // nhead, dtype=torch.float32, device=dev)
+    arr = C.c_void_p * n
+    tk_idx, tk_sc, ia, sa = [], [], None, None
+    if return_topk:
+        ia, sa = arr(), arr()
+        for i in range(n - 1 if n > 1 else 1):
+            l = n - 1 - i
+            shp = (B, d.qh[l] * d.qw[l], int(topks[i]), nhead)
+            tk_idx.append(torch.empty(shp, dtype=torch.int64, device=dev))
+            tk_sc.append(torch.empty(shp, dtype=torch.float32, device=dev))
+            ia[i], sa[i] = tk_idx[-1].data_ptr(), tk_sc[-1].data_ptr()
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_qtatt_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            check(-1, 'casmtr_qtatt_workspace_bytes')
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_qtatt_tokens_fwd(C.byref(d), _ptr(q0), _ptr(k0), _ptr(v0), _ptr(weight if d.type == 0 else None), _ptr(out),
+                                            ia, sa, _ptr(ws), ws.numel(), _stream(out)), 'casmtr_qtatt_tokens_fwd')
+    if return_topk:
+        return out, tk_idx, tk_sc
+    return out
+
+
+def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True, hw_q=None, hw_k=None):
+    """Fused CascadeQTAttB forward -> (message [B,h0*w0,C], upsampled_idx [B,h0*w0,4k] int64 or None).
+    query / key / value: NCHW maps, or - with hw_q / hw_k given - token-major [B, h*w, C] (no transposes)."""
     _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(value, 'value', torch.float32)
     _chk(topk_pos, 'topk_pos', torch.int64)
-    B, Cc, h0, w0 = query.shape
-    h1, w1 = key.shape[2:]
+    tokens = hw_q is not None
+    if tokens:
+        (h0, w0), (h1, w1) = hw_q, hw_k if hw_k is not None else hw_q
+        B, _, Cc = query.shape
+        if query.shape != (B, h0 * w0, Cc) or key.shape != (B, h1 * w1, Cc) or value.shape != key.shape:
+            raise RuntimeError('token-major query/key/value do not match hw_q / hw_k')
+    else:
+        B, Cc, h0, w0 = query.shape
+        h1, w1 = key.shape[2:]
     k = topk_pos.shape[2]
     if topk_pos.shape != (B, (h0 // 2) * (w0 // 2), k, 2):
         raise RuntimeError(f'topk_pos must be [B,(h0/2)*(w0/2),k,2], got {tuple(topk_pos.shape)}')
@@ -178,9 +233,10 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
     with torch.cuda.device(dev):
         nbytes = lib().casmtr_cascade_qtatt_workspace_bytes(B, Cc, h0, w0, h1, w1)
         ws = _workspace(nbytes, dev)
-        check(lib().casmtr_cascade_qtatt_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), _ptr(rel_pos), _ptr(msg), _ptr(up),
-                                             B, nhead, Cc // nhead, h0, w0, h1, w1, k, 1 if dilated is None else int(dilated),
-                                             _ptr(ws), ws.numel(), _stream(msg)), 'casmtr_cascade_qtatt_fwd')
+        fn = lib().casmtr_cascade_qtatt_tokens_fwd if tokens else lib().casmtr_cascade_qtatt_fwd
+        check(fn(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), _ptr(rel_pos), _ptr(msg), _ptr(up),
+                 B, nhead, Cc // nhead, h0, w0, h1, w1, k, 1 if dilated is None else int(dilated),
+                 _ptr(ws), ws.numel(), _stream(msg)), 'casmtr_cascade_qtatt_fwd')
     return msg, up
 
 

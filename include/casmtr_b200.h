@@ -143,6 +143,16 @@ CASMTR_API int casmtr_qtatt_fwd(const casmtr_qtatt_desc *desc,
                      int64_t *const *topk_idx_out, float *const *topk_score_out,
                      void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* Token-major entry (SURVEY 8f "next" #2; src/model/modules/quadtree_attention.py:68-99): q0 / k0 / v0 are the FINEST level
+ * only, token-major [B, h*w, C] fp32 (what a 1x1 convolution is when applied as a linear layer to the [B,N,C] tokens
+ * QuadtreeAttention.forward receives).  The avg_pool2d(2,2) pyramid (:86-89) is built inside, in the layout the kernels
+ * read, so neither the NCHW maps, nor their transposes, nor the caller's pooling launches exist.  desc as above
+ * (qh[l] = qh[l-1] / 2 ...); same workspace size; other arguments as casmtr_qtatt_fwd. */
+CASMTR_API int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *desc, const float *q0, const float *k0, const float *v0,
+                     const float *level_weight, float *out,
+                     int64_t *const *topk_idx_out, float *const *topk_score_out,
+                     void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- fused cascade window attention (R5) */
 
 CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1);
@@ -151,6 +161,14 @@ CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int
  * the previous level); rel_pos NULL or [B,nhead,h0*w0,4k]; message [B,h0*w0,C];
  * upsampled_idx NULL or [B,h0*w0,4k] int64.  k <= 32, D == 32. */
 CASMTR_API int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
+                             const int64_t *topk_pos, const float *rel_pos,
+                             float *message, int64_t *upsampled_idx,
+                             int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
+/* Same with token-major query [B,h0*w0,C] / key, value [B,h1*w1,C] (CascadeQuadtreeAttention.forward,
+ * src/model/modules/quadtree_attention.py:152-171, with the 1x1 convolutions applied as linear layers): no transposes. */
+CASMTR_API int casmtr_cascade_qtatt_tokens_fwd(const float *query, const float *key, const float *value,
                              const int64_t *topk_pos, const float *rel_pos,
                              float *message, int64_t *upsampled_idx,
                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
