@@ -54,6 +54,7 @@ SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_cascade_qtatt_tokens_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                         + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_set_pdl': (C.c_int, [C.c_int]),
     'casmtr_cascade_qtatt_workspace_bytes': (C.c_size_t, [C.c_int] * 6),
     'casmtr_cascade_qtatt_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                  + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),

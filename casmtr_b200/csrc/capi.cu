@@ -1,5 +1,6 @@
 // extern "C" entry points of libcasmtr_b200.so (see include/casmtr_b200.h): argument validation,
 // workspace carving and kernel sequencing.  No allocation, no synchronisation, caller's stream.
+#include <cstdlib>
 #include <stdarg.h>
 #include <string.h>
 
@@ -29,6 +30,22 @@ std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 const char *const g_kind_names[CASMTR_K_COUNT] = {"layout", "qt_coarse", "qt_fine_mid", "qt_fine_last", "cascade_att",
                                                   "cascade_match", "extract", "fine_match", "ops", "cascade_fallback", "coarse_match"};
 }  // namespace
+
+static std::atomic<int> g_pdl{-1};
+bool casmtr_pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("CASMTR_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+int casmtr_set_pdl(int on) {
+    const int prev = casmtr_pdl_enabled() ? 1 : 0;
+    g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}
 
 void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -236,11 +253,13 @@ int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const f
     for (int l = 1; l < d->levels; ++l) {
         PoolJobs pj;
         pj.n = 3;
-        pj.job[0] = PoolJob{bf.q[l - 1], bf.q[l], d->qh[l - 1], d->qw[l - 1]};
-        pj.job[1] = PoolJob{bf.k[l - 1], bf.k[l], d->kh[l - 1], d->kw[l - 1]};
-        pj.job[2] = PoolJob{bf.v[l - 1], bf.v[l], d->kh[l - 1], d->kw[l - 1]};
-        rc = launch_pool_tokens(pj, d->B, C, stream);
+        const bool two = l + 1 < d->levels && d->qh[l - 1] % 4 == 0 && d->qw[l - 1] % 4 == 0 && d->kh[l - 1] % 4 == 0 && d->kw[l - 1] % 4 == 0;
+        pj.job[0] = PoolJob{bf.q[l - 1], bf.q[l], d->qh[l - 1], d->qw[l - 1], two ? bf.q[l + 1] : nullptr};
+        pj.job[1] = PoolJob{bf.k[l - 1], bf.k[l], d->kh[l - 1], d->kw[l - 1], two ? bf.k[l + 1] : nullptr};
+        pj.job[2] = PoolJob{bf.v[l - 1], bf.v[l], d->kh[l - 1], d->kw[l - 1], two ? bf.v[l + 1] : nullptr};
+        rc = two ? launch_pool2_tokens(pj, d->B, C, stream) : launch_pool_tokens(pj, d->B, C, stream);
         if (rc != CASMTR_OK) return rc;
+        if (two) ++l;
     }
     return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
 }

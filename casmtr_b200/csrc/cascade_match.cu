@@ -155,6 +155,7 @@ __device__ __forceinline__ void match_row(const MatchParams &p, const Dir &d, si
 
 template <int NQ>
 __global__ void __launch_bounds__(256) cascade_match_row_kernel(MatchParams p) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t rows0 = (size_t)p.B * p.L0, rows1 = (size_t)p.B * p.L1;
@@ -179,6 +180,7 @@ __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, si
 // CH = 16-byte chunks per feature row (C / 4): 32 or 16.  lane = candidate in the compute phase.
 template <int CH>
 __global__ void __launch_bounds__(256) cascade_match_cell_kernel(MatchParams p, int warps_per_cta) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *slab = smem + (size_t)warp * cell_slab_floats(p.K, 4 * CH);
@@ -366,13 +368,13 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
             if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
             attr_set = true;
         }
-        if (p.C == 128) cascade_match_cell_kernel<32><<<blocks, wpc * 32, smem, stream>>>(q, wpc);
-        else cascade_match_cell_kernel<16><<<blocks, wpc * 32, smem, stream>>>(q, wpc);
+        if (p.C == 128) launch_k(cascade_match_cell_kernel<32>, blocks, wpc * 32, smem, stream, q, wpc);
+        else launch_k(cascade_match_cell_kernel<16>, blocks, wpc * 32, smem, stream, q, wpc);
     } else {
         const unsigned blocks = (unsigned)((rows + 7) / 8);
-        if (p.C <= 128) cascade_match_row_kernel<1><<<blocks, 256, 0, stream>>>(p);
-        else if (p.C <= 256) cascade_match_row_kernel<2><<<blocks, 256, 0, stream>>>(p);
-        else cascade_match_row_kernel<4><<<blocks, 256, 0, stream>>>(p);
+        if (p.C <= 128) launch_k(cascade_match_row_kernel<1>, blocks, 256, 0, stream, p);
+        else if (p.C <= 256) launch_k(cascade_match_row_kernel<2>, blocks, 256, 0, stream, p);
+        else launch_k(cascade_match_row_kernel<4>, blocks, 256, 0, stream, p);
     }
     CASMTR_CHECK_LAUNCH("cascade_match_kernel");
     return CASMTR_OK;

@@ -55,6 +55,7 @@ constexpr int SM_TOTAL = SM_BAR + 4 * 8;
 __global__ void __launch_bounds__((NCONS + 1) * 32, 1)     // 17 warps: one SM sub-partition holds 5 of them, which caps the kernel at 96 registers
 cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, TileParams p) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // 128B-swizzled TMA tiles want 1024-byte alignment
     uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + 2;
@@ -327,7 +328,7 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     CASMTR_REQUIRE(n_work < 0x7fffffffLL, CASMTR_E_UNSUPPORTED, "cascade tile grid too large");
     const unsigned grid = (unsigned)(n_work < n_sm ? n_work : n_sm);          // persistent: one CTA per SM
     LaunchScope ls(CASMTR_K_CASCADE_ATT, stream);
-    cascade_att_tile_kernel<<<grid, (NCONS + 1) * 32, smem, stream>>>(tmK, tmV, tmQ, p);
+    launch_k(cascade_att_tile_kernel, grid, (NCONS + 1) * 32, smem, stream, tmK, tmV, tmQ, p);
     CASMTR_CHECK_LAUNCH("cascade_att_tile_kernel");
     return CASMTR_OK;
 }

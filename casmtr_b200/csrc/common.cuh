@@ -40,6 +40,29 @@ struct LaunchScope {
     ~LaunchScope() { if (slot >= 0) casmtr_prof_end(slot, stream); }
 };
 
+// ---- programmatic dependent launch.  Every hot-path kernel starts with pdl_sync(): it lets the NEXT kernel of the stream be
+// scheduled onto SMs as this grid's tail frees them (griddepcontrol.launch_dependents) and then waits until the PREVIOUS
+// grid has completed and flushed (griddepcontrol.wait) before touching memory -- launch latency and CTA ramp-up overlap the
+// predecessor's tail, the data dependency stays a full one.  launch_k() sets the matching launch attribute
+// (CASMTR_PDL=0 in the environment turns it off; without the attribute both instructions are no-ops).
+bool casmtr_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = casmtr_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

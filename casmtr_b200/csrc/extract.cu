@@ -93,6 +93,7 @@ __device__ __forceinline__ bool keep_token(const ExtractArgs &a, int b, int i) {
 }
 
 __global__ void __launch_bounds__(BLK) extract_mask_kernel(ExtractArgs a) {
+    pdl_sync();
     __shared__ int cnt;
     const int L0 = a.d.h0 * a.d.w0;
     const size_t n = (size_t)a.d.B * L0;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(BLK) extract_mask_kernel(ExtractArgs a) {
 }
 
 __global__ void __launch_bounds__(1024) extract_scan_kernel(ExtractArgs a, int nblocks, int32_t *count_out) {
+    pdl_sync();
     __shared__ int warp_tot[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -174,6 +176,7 @@ __device__ __forceinline__ void emit(const ExtractArgs &a, const EmitOut &e, int
 }
 
 __global__ void __launch_bounds__(BLK) extract_emit_kernel(ExtractArgs a, EmitOut e) {
+    pdl_sync();
     __shared__ int warp_cnt[BLK / 32];
     const int L0 = a.d.h0 * a.d.w0;
     const size_t n = (size_t)a.d.B * L0;
@@ -273,12 +276,12 @@ int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01,
         cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream);
         return CASMTR_OK;
     }
-    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_mask_kernel<<<nb, BLK, 0, stream>>>(a); }
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); launch_k(extract_mask_kernel, nb, BLK, 0, stream, a); }
     CASMTR_CHECK_LAUNCH("extract_mask_kernel");
-    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_scan_kernel<<<1, 1024, 0, stream>>>(a, nb, count_out); }
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); launch_k(extract_scan_kernel, 1, 1024, 0, stream, a, nb, count_out); }
     CASMTR_CHECK_LAUNCH("extract_scan_kernel");
     EmitOut e{mask_out, b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, capacity};
-    { LaunchScope ls(CASMTR_K_EXTRACT, stream); extract_emit_kernel<<<nb, BLK, 0, stream>>>(a, e); }
+    { LaunchScope ls(CASMTR_K_EXTRACT, stream); launch_k(extract_emit_kernel, nb, BLK, 0, stream, a, e); }
     CASMTR_CHECK_LAUNCH("extract_emit_kernel");
     return CASMTR_OK;
 }

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const float *__restrict
                                                           const int64_t *__restrict__ b_ids, float scale,
                                                           float *__restrict__ expec_f, float *__restrict__ mkpts1_f,
                                                           int M, int WW, int W, int C) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
@@ -96,7 +97,7 @@ int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, c
     CASMTR_REQUIRE(C % 4 == 0 && C > 0, CASMTR_E_UNSUPPORTED, "fine_match: C=%d must be a positive multiple of 4", C);
     if (M == 0) return CASMTR_OK;
     LaunchScope ls(CASMTR_K_FINE_MATCH, stream);
-    fine_match_kernel<<<(M + 7) / 8, 256, 0, stream>>>(f0, f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, W, C);
+    launch_k(fine_match_kernel, (M + 7) / 8, 256, 0, stream, f0, f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, W, C);
     CASMTR_CHECK_LAUNCH("fine_match_kernel");
     return CASMTR_OK;
 }

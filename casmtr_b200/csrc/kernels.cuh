@@ -18,12 +18,14 @@ struct PoolJob {
     const float *src;   // [B, h*w, C] token-major
     float *dst;         // [B, (h/2)*(w/2), C]
     int h, w;
+    float *dst2;        // launch_pool2_tokens only: [B, (h/4)*(w/4), C]
 };
 struct PoolJobs {
     PoolJob job[3];
     int n;
 };
 int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream);
+int launch_pool2_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream);
 int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
                        size_t n_tok, int nh, int k, cudaStream_t stream);
 

@@ -52,6 +52,7 @@ struct VecJobs {
 };
 
 __global__ void __launch_bounds__(256) transpose_vec_kernel(VecJobs jobs) {
+    pdl_sync();
     int t = blockIdx.x;
     int j = 0;
 #pragma unroll 1
@@ -93,7 +94,7 @@ int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
         vj.blk_begin[jobs.n] = total;
         if (total == 0) return CASMTR_OK;
         LaunchScope ls(CASMTR_K_LAYOUT, stream);
-        transpose_vec_kernel<<<dim3(total, B), 256, 0, stream>>>(vj);
+        launch_k(transpose_vec_kernel, dim3(total, B), 256, 0, stream, vj);
         CASMTR_CHECK_LAUNCH("transpose_vec_kernel");
         return CASMTR_OK;
     }
@@ -114,6 +115,7 @@ int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
 // QuadtreeAttention.forward (src/model/modules/quadtree_attention.py:86-89, F.avg_pool2d(kernel 2, stride 2)); the four
 // taps are summed in avg_pool2d's window order.  Thread = 4 channels of one output token; up to 3 maps (q, k, v) per launch.
 __global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4) {
+    pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
     const int ho = jb.h >> 1, wo = jb.w >> 1;
@@ -134,6 +136,57 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4)
     }
 }
 
+// Two pyramid levels in one pass (h, w multiples of 4): thread = 4 channels of one level-2 token; its 4x4 block of level-0
+// tokens is read once, the four level-1 averages are written and averaged again (the reference pools the pooled map).
+__global__ void __launch_bounds__(256) pool2_tokens_kernel(PoolJobs jobs, int C4) {
+    pdl_sync();
+    const int j = blockIdx.z, b = blockIdx.y;
+    const PoolJob jb = jobs.job[j];
+    const int h1 = jb.h >> 1, w1 = jb.w >> 1, h2 = jb.h >> 2, w2 = jb.w >> 2;
+    const size_t n = (size_t)h2 * w2 * C4;
+    const float4 *src = reinterpret_cast<const float4 *>(jb.src) + (size_t)b * jb.h * jb.w * C4;
+    float4 *d1 = reinterpret_cast<float4 *>(jb.dst) + (size_t)b * h1 * w1 * C4;
+    float4 *d2 = reinterpret_cast<float4 *>(jb.dst2) + (size_t)b * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int t = (int)(i / C4), y = t / w2, x = t - y * w2;
+        float4 m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int y1 = 2 * y + (q >> 1), x1 = 2 * x + (q & 1);
+            const float4 *p = src + ((size_t)(2 * y1) * jb.w + 2 * x1) * C4 + c;
+            const float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)jb.w * C4), d = __ldg(p + (size_t)(jb.w + 1) * C4);
+            m[q].x = (((a.x + bb.x) + cc.x) + d.x) * 0.25f;
+            m[q].y = (((a.y + bb.y) + cc.y) + d.y) * 0.25f;
+            m[q].z = (((a.z + bb.z) + cc.z) + d.z) * 0.25f;
+            m[q].w = (((a.w + bb.w) + cc.w) + d.w) * 0.25f;
+            d1[((size_t)y1 * w1 + x1) * C4 + c] = m[q];
+        }
+        float4 o;
+        o.x = (((m[0].x + m[1].x) + m[2].x) + m[3].x) * 0.25f;
+        o.y = (((m[0].y + m[1].y) + m[2].y) + m[3].y) * 0.25f;
+        o.z = (((m[0].z + m[1].z) + m[2].z) + m[3].z) * 0.25f;
+        o.w = (((m[0].w + m[1].w) + m[2].w) + m[3].w) * 0.25f;
+        d2[i] = o;
+    }
+}
+
+int launch_pool2_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) {
+    if (jobs.n == 0 || B == 0) return CASMTR_OK;
+    CASMTR_REQUIRE(C % 4 == 0, CASMTR_E_UNSUPPORTED, "pool_tokens: C=%d must be a multiple of 4", C);
+    size_t nmax = 0;
+    for (int i = 0; i < jobs.n; ++i) {
+        CASMTR_REQUIRE((((uintptr_t)jobs.job[i].src | (uintptr_t)jobs.job[i].dst | (uintptr_t)jobs.job[i].dst2) & 15) == 0, CASMTR_E_INVALID, "pool_tokens: unaligned map");
+        CASMTR_REQUIRE(jobs.job[i].h % 4 == 0 && jobs.job[i].w % 4 == 0, CASMTR_E_INVALID, "pool2_tokens: grid not a multiple of 4");
+        nmax = std::max(nmax, (size_t)(jobs.job[i].h / 4) * (jobs.job[i].w / 4) * (C / 4));
+    }
+    if (nmax == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
+    launch_k(pool2_tokens_kernel, dim3((unsigned)std::min<size_t>((nmax + 255) / 256, 148 * 8), B, jobs.n), 256, 0, stream, jobs, C / 4);
+    CASMTR_CHECK_LAUNCH("pool2_tokens_kernel");
+    return CASMTR_OK;
+}
+
 int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) {
     if (jobs.n == 0 || B == 0) return CASMTR_OK;
     CASMTR_REQUIRE(C % 4 == 0, CASMTR_E_UNSUPPORTED, "pool_tokens: C=%d must be a multiple of 4", C);
@@ -144,7 +197,7 @@ int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) 
     }
     if (nmax == 0) return CASMTR_OK;
     LaunchScope ls(CASMTR_K_LAYOUT, stream);
-    pool_tokens_kernel<<<dim3((unsigned)std::min<size_t>((nmax + 255) / 256, 148 * 8), B, jobs.n), 256, 0, stream>>>(jobs, C / 4);
+    launch_k(pool_tokens_kernel, dim3((unsigned)std::min<size_t>((nmax + 255) / 256, 148 * 8), B, jobs.n), 256, 0, stream, jobs, C / 4);
     CASMTR_CHECK_LAUNCH("pool_tokens_kernel");
     return CASMTR_OK;
 }
@@ -153,6 +206,7 @@ int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) 
 __global__ void topk_to_api_kernel(const int *__restrict__ idx, const float *__restrict__ score,
                                    int64_t *__restrict__ idx_out, float *__restrict__ score_out,
                                    size_t n_tok, int nh, int k) {
+    pdl_sync();
     const size_t total = n_tok * nh * k;
     for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
         const int h = (int)(o % nh);
@@ -171,7 +225,7 @@ int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, flo
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     LaunchScope ls(CASMTR_K_LAYOUT, stream);
-    topk_to_api_kernel<<<blocks, 256, 0, stream>>>(idx, score, idx_out, score_out, n_tok, nh, k);
+    launch_k(topk_to_api_kernel, blocks, 256, 0, stream, idx, score, idx_out, score_out, n_tok, nh, k);
     CASMTR_CHECK_LAUNCH("topk_to_api_kernel");
     return CASMTR_OK;
 }

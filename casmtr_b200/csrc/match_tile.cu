@@ -39,6 +39,7 @@ constexpr int SM_TOTAL = SM_BAR + 2 * NSTAGE * 8;
 struct Maps { CUtensorMap key[2], qry[2]; };              // [direction]: key image / query image feature maps
 
 __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel(const __grid_constant__ Maps maps, MatchParams p) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + NSTAGE;
@@ -271,7 +272,7 @@ int launch_cascade_match_tile(const MatchParams &p, cudaStream_t stream) {
     const long long n_work = (long long)p.B * (tiles0 + tiles1);
     const unsigned grid = (unsigned)(n_work < n_sm ? n_work : n_sm);
     LaunchScope ls(CASMTR_K_CASCADE_MATCH, stream);
-    cascade_match_tile_kernel<<<grid, (NCONS + 1) * 32, smem, stream>>>(maps, p);
+    launch_k(cascade_match_tile_kernel, grid, (NCONS + 1) * 32, smem, stream, maps, p);
     CASMTR_CHECK_LAUNCH("cascade_match_tile_kernel");
     return CASMTR_OK;
 }

@@ -217,6 +217,7 @@ __device__ __forceinline__ void rows_softmax_topk(float *const (&srow)[RP], cons
 
 template <int ROWS>
 __global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
+    pdl_sync();
     constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16, 4 for 8)
     constexpr int TOK_PER_WARP = TILE / NW;        // 8
     extern __shared__ __align__(16) float smem[];
@@ -504,9 +505,9 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
     }
     dim3 grid((p.Sq + rows - 1) / rows, p.B * p.nh);
     LaunchScope ls(CASMTR_K_QT_COARSE, stream);
-    if (rows == 32) qtatt_coarse_kernel<32><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
-    else if (rows == 16) qtatt_coarse_kernel<16><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
-    else qtatt_coarse_kernel<8><<<grid, NW * 32, smem, stream>>>(p, coarse_s_ld(p.Sk));
+    if (rows == 32) launch_k(qtatt_coarse_kernel<32>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
+    else if (rows == 16) launch_k(qtatt_coarse_kernel<16>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
+    else launch_k(qtatt_coarse_kernel<8>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
     CASMTR_CHECK_LAUNCH("qtatt_coarse_kernel");
     return CASMTR_OK;
 }

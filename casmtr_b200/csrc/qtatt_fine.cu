@@ -402,6 +402,7 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
 // is consumed downstream, and every comparison in tests/ is on sets).
 template <int KP, int R, bool TYPE_A, bool DO_TOPK>
 __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;       // warp = sibling f
     const int g = lane >> 3, dq = lane & 7;
@@ -614,7 +615,7 @@ int launch_cta_t(const FineParams &p, cudaStream_t stream) {
         attr_set = true;
     }
     LaunchScope ls(DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST, stream);
-    kern<<<dim3((unsigned)items, p.B), 128, smem, stream>>>(p);
+    launch_k(kern, dim3((unsigned)items, p.B), 128, smem, stream, p);
     CASMTR_CHECK_LAUNCH("quad_cta_kernel");
     return CASMTR_OK;
 }
@@ -622,6 +623,7 @@ int launch_cta_t(const FineParams &p, cudaStream_t stream) {
 // grid.x covers the (parent, head) items of one batch element, grid.y = batch
 template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
 __global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int warps_per_cta) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Np = (p.h0 >> 1) * (p.w0 >> 1);
@@ -634,6 +636,7 @@ __global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int w
 // persistent variant over a device-side list of cells (b * Np + parent), all heads of each: the cascade fallback
 template <int KP, int R>
 __global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, int warps_per_cta) {
+    pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Np = (p.h0 >> 1) * (p.w0 >> 1);
@@ -666,7 +669,7 @@ int launch_t(const FineParams &p, cudaStream_t stream) {
         attr_set = true;
     }
     LaunchScope ls(CASCADE ? CASMTR_K_CASCADE_ATT : (DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST), stream);
-    kern<<<dim3((unsigned)blocks, p.B), wpc * 32, smem, stream>>>(p, wpc);
+    launch_k(kern, dim3((unsigned)blocks, p.B), wpc * 32, smem, stream, p, wpc);
     CASMTR_CHECK_LAUNCH("quad_attention_kernel");
     return CASMTR_OK;
 }
@@ -686,7 +689,7 @@ int launch_list_t(const FineParams &p, cudaStream_t stream) {
         attr_set = true;
     }
     LaunchScope ls(CASMTR_K_CASCADE_FALLBACK, stream);
-    kern<<<2 * 148, wpc * 32, smem, stream>>>(p, wpc);             // persistent: the list length is only known on the device
+    launch_k(kern, 2 * 148, wpc * 32, smem, stream, p, wpc);             // persistent: the list length is only known on the device
     CASMTR_CHECK_LAUNCH("quad_attention_list_kernel");
     return CASMTR_OK;
 }

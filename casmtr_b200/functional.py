@@ -46,6 +46,11 @@ def profile_enable(on=True):
     check(lib().casmtr_profile_enable(1 if on else 0), 'casmtr_profile_enable')
 
 
+def set_pdl(on):
+    """Programmatic dependent launch of the hot-path kernels on/off (casmtr_set_pdl); returns the previous setting."""
+    return bool(lib().casmtr_set_pdl(1 if on else 0))
+
+
 def profile_collect():
     """-> {kind_name: (device_ms, launches)} accumulated since the last collect (synchronises)."""
     ms = (C.c_double * _lib.K_COUNT)()

@@ -15,6 +15,7 @@ tests and smoke() all drive the path through this one class, via the public modu
 import torch
 import torch.nn as nn
 
+from . import functional as F
 from . import synth
 from .cascade_matching import CascadeMatching
 from .fine_matching import CascadeFineMatching
@@ -201,8 +202,14 @@ class GraphRunner:
             torch.cuda.synchronize(dev)
             self.side = torch.cuda.Stream(dev) if two_streams else None
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body(self.side)
+            # with two concurrent streams the other direction's kernel already fills a kernel's tail; early-scheduled
+            # dependent CTAs would only hold SM resources it could use (measured: 2.45 ms vs 2.39 ms per step)
+            prev = F.set_pdl(not two_streams)
+            try:
+                with torch.cuda.graph(self.graph):
+                    self._body(self.side)
+            finally:
+                F.set_pdl(prev)
             self.deferred = self.data['stage_4c']['_deferred']      # static buffers the graph writes on every replay
         finally:
             hp.matching.defer_sync = False

@@ -153,6 +153,13 @@ CASMTR_API int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *desc, const floa
                      int64_t *const *topk_idx_out, float *const *topk_score_out,
                      void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* Programmatic dependent launch: when on (default; CASMTR_PDL=0 in the environment turns it off) every hot-path kernel is
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the previous kernel of the
+ * stream drains and wait (griddepcontrol.wait) for its completion before touching memory.  Helps back-to-back launches on ONE
+ * stream; turn it off when independent calls already overlap on several streams (waiting CTAs hold SM resources the other
+ * stream could use).  Returns the previous setting. */
+CASMTR_API int casmtr_set_pdl(int on);
+
 /* ---------------------------------------------------------------- fused cascade window attention (R5) */
 
 CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1);
