@@ -165,6 +165,72 @@ def gen_windows(ref):
     save('windows', idx=idx, hw=torch.tensor([H, W]), pos=pos)
 
 
+def gen_widen(ref):
+    """SURVEY section 8f "next" rows: the reference's CoarseMatching, CascadeFinePreprocess, QuadtreeAttention and
+    CascadeQuadtreeAttention modules, unmodified, on seeded inputs (weights stored next to the outputs)."""
+    import importlib
+    g = torch.Generator().manual_seed(11)
+    # -- CoarseMatching (dense dual softmax at 1/8)
+    cmod = importlib.import_module('src.model.functions.coarse_matching')
+    B, h, w, C = 2, 12, 16, 64
+    f0 = torch.randn(B, h * w, C, generator=g)
+    f1 = 0.8 * f0[:, torch.randperm(h * w, generator=g)] + 0.6 * torch.randn(B, h * w, C, generator=g)
+    cfg = {'thr': 0.2, 'border_rm': 2, 'train_coarse_percent': 0.3, 'train_pad_num_gt_min': 200, 'match_type': 'dual_softmax',
+           'dsmax_temperature': 0.1}
+    data = {'hw0_i': (h * 8, w * 8), 'hw1_i': (h * 8, w * 8), 'hw0_8c': (h, w), 'hw1_8c': (h, w), 'bs': B}
+    m = cmod.CoarseMatching(cfg).eval()
+    with torch.no_grad():
+        m(f0, f1, data)
+    st = data['stage_8c']
+    save('widen_coarse_match', feat0=f0, feat1=f1, temperature=torch.tensor(0.1), next_conf01=st['next_conf_c01'], next_idx01=st['next_idx_c01'],
+         next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'])
+    # -- CascadeFinePreprocess
+    fmod = importlib.import_module('src.model.functions.fine_matching')
+    Bf, Cf, Cc, hc, wc, stride, M = 2, 32, 64, 10, 14, 2, 40
+    ff0, ff1 = torch.randn(Bf, Cf, hc * stride, wc * stride, generator=g), torch.randn(Bf, Cf, hc * stride, wc * stride, generator=g)
+    fc0, fc1 = torch.randn(Bf, hc * wc, Cc, generator=g), torch.randn(Bf, hc * wc, Cc, generator=g)
+    b_ids = torch.randint(0, Bf, (M,), generator=g).sort()[0]
+    i_ids, j_ids = torch.randint(0, hc * wc, (M,), generator=g), torch.randint(0, hc * wc, (M,), generator=g)
+    i_ids[:4] = torch.tensor([0, wc - 1, (hc - 1) * wc, hc * wc - 1])
+    out = {}
+    for cat in (False, True):
+        torch.manual_seed(12)
+        pm = fmod.CascadeFinePreprocess({'fine_concat_coarse_feat': cat, 'fine_window_size': 5}, {'d_model': Cf}, {'d_model': Cc}, '4c').eval()
+        d = {'hw0_f': (hc * stride, wc * stride), 'hw0_4c': (hc, wc), 'hw1_4c': (hc, wc), 'stage_4c': {'b_ids': b_ids, 'i_ids': i_ids, 'j_ids': j_ids}}
+        with torch.no_grad():
+            o0, o1 = pm(ff0, ff1, fc0, fc1, d)
+        tag = 'cat' if cat else 'plain'
+        out[f'{tag}_out0'], out[f'{tag}_out1'] = o0, o1
+        if cat:
+            out.update({'w_' + k.replace('.', '_'): v for k, v in pm.state_dict().items()})
+    save('widen_fine_preprocess', feat_f0=ff0, feat_f1=ff1, feat_c0=fc0, feat_c1=fc1, b_ids=b_ids, i_ids=i_ids, j_ids=j_ids,
+         hw_c=torch.tensor([hc, wc]), stride=torch.tensor(stride), **out)
+    # -- QuadtreeAttention (B and A) and CascadeQuadtreeAttention
+    amod = importlib.import_module('src.model.modules.quadtree_attention')
+    Ba, Ca, nh, H, W, topks = 1, 64, 2, 16, 24, [8, 4, 4]
+    x, t = torch.randn(Ba, H * W, Ca, generator=g), torch.randn(Ba, H * W, Ca, generator=g)
+    out = {}
+    for typ in ('B',):        # attn_type='A' cannot run in the reference (QTAttA.forward takes no rel_pos, quadtree_attention.py:94)
+        torch.manual_seed(13)
+        layer = amod.QuadtreeAttention(Ca, nh, topks, scale=3, attn_type=typ).eval()
+        for p in (layer.q_proj, layer.k_proj, layer.v_proj):
+            torch.nn.init.normal_(p.weight, std=0.12, generator=g)       # spread logits; the default std 0.02 gives flat softmaxes
+        with torch.no_grad():
+            out[f'out_{typ}'] = layer(x, t, H, W)
+        out.update({f'{typ}_' + k.replace('.', '_'): v for k, v in layer.state_dict().items()})
+    d = synth.cascade_inputs(1, Ca, 16, 16, seed=105)
+    xc, tc = d['feat0'].flatten(2).transpose(1, 2).contiguous(), d['feat1'].flatten(2).transpose(1, 2).contiguous()
+    torch.manual_seed(14)
+    cl = amod.CascadeQuadtreeAttention(Ca, nh, dilated=1).eval()
+    for p in (cl.q_proj, cl.k_proj, cl.v_proj):
+        torch.nn.init.normal_(p.weight, std=0.12, generator=g)
+    with torch.no_grad():
+        co, cup = cl(xc, tc, 16, 16, idx=d['topk_pos01'])
+    out.update({'C_' + k.replace('.', '_'): v for k, v in cl.state_dict().items()})
+    save('widen_attention_layers', x=x, target=t, hw=torch.tensor([H, W]), topks=torch.tensor(topks), nhead=torch.tensor(nh),
+         cas_x=xc, cas_target=tc, cas_topk_pos=d['topk_pos01'], cas_out=co, cas_upsampled_idx=cup, **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -174,3 +240,4 @@ if __name__ == '__main__':
     gen_cascade_match(ref)
     gen_fine(ref)
     gen_windows(ref)
+    gen_widen(ref)

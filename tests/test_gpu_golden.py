@@ -98,3 +98,65 @@ def test_fine_matching_vs_reference(dev):
         casmtr_b200.CascadeFineMatching('4c').eval()(g['feat_f0'].to(dev), g['feat_f1'].to(dev), data)
         assert (data['expec_f'].cpu() - g['plain_expec_f']).abs().max() < 1e-5
         assert (data['mkpts1_f'].cpu() - g[f'{tag}_mkpts1_f']).abs().max() < 1e-4
+
+
+# ---- SURVEY section 8f "next" rows against the reference's own modules (tests/golden/widen_*.npz)
+def _load_sd(mod, g, prefix):
+    sd = {}
+    for k in mod.state_dict():
+        sd[k] = g[prefix + k.replace('.', '_')]
+    mod.load_state_dict(sd)                                    # the reference's state-dict keys, unchanged
+    return mod
+
+
+def test_coarse_matching_vs_reference(dev):
+    g = load('widen_coarse_match')
+    cfg = {'thr': 0.2, 'border_rm': 2, 'train_coarse_percent': 0.3, 'train_pad_num_gt_min': 200, 'match_type': 'dual_softmax',
+           'dsmax_temperature': float(g['temperature'])}
+    data = {'hw0_i': (96, 128), 'hw1_i': (96, 128), 'hw0_8c': (12, 16), 'hw1_8c': (12, 16), 'bs': 2}
+    casmtr_b200.CoarseMatching(cfg).eval()(g['feat0'].to(dev), g['feat1'].to(dev), data)
+    st = data['stage_8c']
+    assert (st['next_conf_c01'].cpu() - g['next_conf01']).abs().max() < TOL and (st['next_conf_c10'].cpu() - g['next_conf10']).abs().max() < TOL
+    # arg-max is specified where the best two logits are apart (3xTF32 products carry ~1e-6 relative error)
+    C = g['feat0'].shape[-1]
+    sim = torch.einsum('nlc,nsc->nls', g['feat0'].double(), g['feat1'].double()) / C / float(g['temperature'])
+    t01, t10 = sim.topk(2, dim=2)[0], sim.topk(2, dim=1)[0]
+    clear01, clear10 = (t01[..., 0] - t01[..., 1]) > 1e-4, (t10[:, 0] - t10[:, 1]) > 1e-4
+    assert clear01.float().mean() > 0.99
+    assert torch.equal(st['next_idx_c01'].cpu()[clear01], g['next_idx01'][clear01])
+    assert torch.equal(st['next_idx_c10'].cpu()[clear10], g['next_idx10'][clear10])
+
+
+@pytest.mark.parametrize('cat', [False, True])
+def test_fine_preprocess_vs_reference(dev, cat):
+    g = load('widen_fine_preprocess')
+    hc, wc = g['hw_c'].tolist()
+    s = int(g['stride'])
+    mod = casmtr_b200.CascadeFinePreprocess({'fine_concat_coarse_feat': cat, 'fine_window_size': 5}, {'d_model': 32}, {'d_model': 64}, '4c').eval()
+    if cat:
+        _load_sd(mod, g, 'w_')
+    data = {'hw0_f': (hc * s, wc * s), 'hw0_4c': (hc, wc), 'hw1_4c': (hc, wc),
+            'stage_4c': {'b_ids': g['b_ids'].to(dev), 'i_ids': g['i_ids'].to(dev), 'j_ids': g['j_ids'].to(dev)}}
+    with torch.no_grad():
+        o0, o1 = mod.to(dev)(g['feat_f0'].to(dev), g['feat_f1'].to(dev), g['feat_c0'].to(dev), g['feat_c1'].to(dev), data)
+    tag = 'cat' if cat else 'plain'
+    if cat:
+        assert (o0.cpu() - g['cat_out0']).abs().max() < TOL and (o1.cpu() - g['cat_out1']).abs().max() < TOL
+    else:
+        assert torch.equal(o0.cpu(), g[f'{tag}_out0']) and torch.equal(o1.cpu(), g[f'{tag}_out1'])       # a gather: bit-exact
+
+
+def test_attention_layers_vs_reference(dev):
+    g = load('widen_attention_layers')
+    H, W = g['hw'].tolist()
+    nh, topks = int(g['nhead']), g['topks'].tolist()
+    layer = _load_sd(casmtr_b200.QuadtreeAttention(64, nh, topks, scale=3, attn_type='B'), g, 'B_').to(dev).eval()
+    with torch.no_grad():
+        out = layer(g['x'].to(dev), g['target'].to(dev), H, W)
+    bad = ((out.cpu() - g['out_B']).abs().amax(dim=2) > 1e-4).float().mean().item()   # GEMM rounding may flip an exact near-tie of the top-k
+    assert bad < 5e-3, bad
+    cl = _load_sd(casmtr_b200.CascadeQuadtreeAttention(64, nh, dilated=1), g, 'C_').to(dev).eval()
+    with torch.no_grad():
+        co, up = cl(g['cas_x'].to(dev), g['cas_target'].to(dev), 16, 16, idx=g['cas_topk_pos'].to(dev))
+    assert torch.equal(up.cpu(), g['cas_upsampled_idx'])
+    assert (co.cpu() - g['cas_out']).abs().max() < TOL
