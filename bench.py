@@ -428,6 +428,15 @@ def run_ours(args):
                 'what': 'QTAttB at 1/8 from token-major level-0 q/k/v with the avg-pool pyramid built inside (casmtr_qtatt_tokens_fwd) '
                         'vs the NCHW pyramid lists of the reference API (casmtr_qtatt_fwd); the reference additionally pays 6 avg_pool2d launches upstream'}
             del tok
+            cc = dev_in['cas'][0]
+            centre = cc['topk_pos'][:, :, 12]                                   # window centre -> an index with the same window
+            nidx = (centre[..., 0] * (wl.w4 // 2) + centre[..., 1]).contiguous()
+            t_pos = _time(lambda: F.cascade_qtatt_forward(cc['q'], cc['k'], cc['v'], cc['topk_pos'], None, wl.nh4))
+            t_idx = _time(lambda: F.cascade_qtatt_forward(cc['q'], cc['k'], cc['v'], nidx, None, wl.nh4))
+            next_rows['cascade_window_fusion'] = {
+                'ms_per_call_topk_pos': t_pos, 'ms_per_call_next_idx': t_idx,
+                'what': 'CascadeQTAttB at 1/4 fed with the expanded window positions [B,L/4,25,2] (reference API) vs with next_idx [B,L/4] '
+                        '(window expansion of get_window_warp_idx fused into the kernels, casmtr_cascade_qtatt_window_fwd)'}
             M = max(n_matches, 1)
             g = torch.Generator().manual_seed(9)
             ff = torch.randn(wl.B, 64, wl.hf, wl.wf, generator=g).to(dev)

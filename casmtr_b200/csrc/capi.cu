@@ -320,7 +320,27 @@ size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1
 static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
                               const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
                               int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
-                              void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx = nullptr, int win = 0);
+
+int casmtr_window_idx_fwd(const int64_t *next_idx, int64_t *pos, int B, int L, int H, int W, int window, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && L >= 0 && window >= 1 && (window & 1) && H >= window && W >= window, CASMTR_E_INVALID,
+                   "window_idx: window %d must be odd and fit the %dx%d grid", window, H, W);
+    CASMTR_REQUIRE((size_t)B * L == 0 || (next_idx && pos), CASMTR_E_INVALID, "window_idx: null pointer");
+    return launch_window_idx(next_idx, pos, (size_t)B * L, H, W, window, (cudaStream_t)stream);
+}
+
+int casmtr_cascade_qtatt_window_fwd(const float *query, const float *key, const float *value,
+                                    const int64_t *next_idx, int window, const float *rel_pos,
+                                    float *message, int64_t *upsampled_idx,
+                                    int B, int nhead, int D, int h0, int w0, int h1, int w1, int token_major,
+                                    void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(window >= 1 && (window & 1) && window * window <= 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt_window: window %d must be 1, 3 or 5", window);
+    CASMTR_REQUIRE(h1 % 2 == 0 && w1 % 2 == 0 && h1 / 2 >= window && w1 / 2 >= window, CASMTR_E_INVALID,
+                   "cascade_qtatt_window: the %dx%d key grid must be even and its parent grid must hold a %d-window", h1, w1, window);
+    CASMTR_REQUIRE(next_idx != nullptr, CASMTR_E_INVALID, "cascade_qtatt_window: null next_idx");
+    return cascade_qtatt_impl(token_major != 0, query, key, value, nullptr, rel_pos, message, upsampled_idx, B, nhead, D, h0, w0, h1, w1,
+                              window * window, 1, workspace, workspace_bytes, (cudaStream_t)stream, next_idx, window);
+}
 
 int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
                              const int64_t *topk_pos, const float *rel_pos,
@@ -343,13 +363,13 @@ int casmtr_cascade_qtatt_tokens_fwd(const float *query, const float *key, const 
 static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
                               const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
                               int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
-                              void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx, int win) {
     CASMTR_REQUIRE(D == 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: head dim %d unsupported (D == 32)", D);
     CASMTR_REQUIRE(B >= 1 && nhead >= 1 && h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0, CASMTR_E_INVALID, "cascade_qtatt: bad sizes");
     CASMTR_REQUIRE(h0 % 2 == 0 && w0 % 2 == 0, CASMTR_E_INVALID, "cascade_qtatt: query grid %dx%d must be even", h0, w0);
     CASMTR_REQUIRE(k >= 1 && k <= 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: window size k=%d must be in [1,32]", k);
     CASMTR_REQUIRE(dilated >= 1, CASMTR_E_INVALID, "cascade_qtatt: dilated=%d", dilated);
-    CASMTR_REQUIRE(query && key && value && topk_pos && message && workspace, CASMTR_E_INVALID, "cascade_qtatt: null pointer");
+    CASMTR_REQUIRE(query && key && value && (topk_pos || next_idx) && message && workspace, CASMTR_E_INVALID, "cascade_qtatt: null pointer");
     const int C = nhead * D;
     Workspace ws(workspace, workspace_bytes);
     const float *qt = query, *kt = key, *vt = value;
@@ -374,14 +394,14 @@ static int cascade_qtatt_impl(bool token_major, const float *query, const float 
     FineParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.q = qt; fp.k = kt; fp.v = vt;
-    fp.topk_pos = topk_pos; fp.rel_pos = rel_pos;
+    fp.topk_pos = topk_pos; fp.next_idx = next_idx; fp.win = win; fp.rel_pos = rel_pos;
     fp.out = message; fp.upsampled_idx = upsampled_idx;
     fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1;
     fp.kp = k; fp.dil = dilated;
     if (k == 25 && dilated == 1 && ((uintptr_t)topk_pos & 15) == 0) {
         // regular 5x5 windows: TMA-tiled kernel for the coherent cells, gather kernel for the listed outliers
         int *fb_count = fb + (size_t)B * (h0 / 2) * (w0 / 2);
-        rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, rel_pos, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
+        rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, next_idx, rel_pos, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
         if (rc != CASMTR_OK) return rc;
         fp.item_list = fb; fp.item_count = fb_count;
     }

@@ -33,6 +33,7 @@ constexpr int KC = 100;
 
 struct TileParams {
     const int64_t *topk_pos;    // [B, Np, 25, 2]
+    const int64_t *next_idx;    // [B, Np] instead of topk_pos: the 5x5 window is derived from the parent's match
     const float *rel_pos;       // [B, nh, h0*w0, 100] or NULL
     float *out;                 // [B, h0*w0, C]
     int64_t *upsampled_idx;     // [B, h0*w0, 100] or NULL
@@ -87,7 +88,12 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             const int64_t *tp = p.topk_pos + ((size_t)b * Np + (size_t)(have ? py * wp + px : 0)) * 50;
             int r0 = 0, c0 = 0;
             bool regular = have;
-            if (have) {
+            if (have && p.next_idx != nullptr) {     // regular by construction: 8 bytes per cell instead of 400
+                const int hv = p.h1 >> 1, wv = p.w1 >> 1;
+                const int idx = (int)__ldg(p.next_idx + (size_t)b * Np + py * wp + px);
+                r0 = window_origin(idx / wv, 5, hv);
+                c0 = window_origin(idx % wv, 5, wv);
+            } else if (have) {
                 const longlong2 w0v = __ldg(reinterpret_cast<const longlong2 *>(tp));
                 r0 = (int)w0v.x;
                 c0 = (int)w0v.y;
@@ -298,7 +304,7 @@ size_t cascade_tile_smem_bytes() { return 1024 + SM_TOTAL; }
 
 // Tile path of CascadeQTAttB for k == 25, dilated == 1.  q/k/v are the token-major copies.  Cells that cannot use their
 // block's tile are appended to fb_list (count in *fb_count, zeroed here); the caller runs the gather kernel over that list.
-int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const float *rel_pos,
+int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const int64_t *next_idx, const float *rel_pos,
                             float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
                             int B, int nh, int h0, int w0, int h1, int w1, cudaStream_t stream) {
     const int C = nh * D;
@@ -308,7 +314,7 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     if (rc == CASMTR_OK) rc = make_tile_map(&tmQ, q, B, h0, w0, C, 2 * TP, 2 * TP, false);
     if (rc != CASMTR_OK) return rc;
     TileParams p;
-    p.topk_pos = topk_pos; p.rel_pos = rel_pos; p.out = out; p.upsampled_idx = upsampled_idx;
+    p.topk_pos = topk_pos; p.next_idx = next_idx; p.rel_pos = rel_pos; p.out = out; p.upsampled_idx = upsampled_idx;
     p.fb_list = fb_list; p.fb_count = fb_count;
     p.B = B; p.nh = nh; p.h0 = h0; p.w0 = w0; p.h1 = h1; p.w1 = w1;
     const int hp = h0 / 2, wp = w0 / 2;

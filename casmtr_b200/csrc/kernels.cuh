@@ -51,6 +51,9 @@ struct FineParams {
     const int *prev_idx;        // [B, Np, nh, kp]   (QTAtt levels)  key index on the (h1/2 x w1/2) grid
     const float *prev_score;    // [B, Np, nh, kp]   (type A only)
     const int64_t *topk_pos;    // [B, Np, kp, 2]    (cascade)  row, col on the previous grid
+    const int64_t *next_idx;    // [B, Np] (cascade, instead of topk_pos): match of the parent cell on the previous grid of the other
+                                // image; the win x win window around it, shifted inside the grid, is derived in the kernel
+    int win;                    // window side (kp == win * win) when next_idx is used
     const float *rel_pos;       // [B, nh, h0*w0, 4kp] or NULL (cascade)
     const float *acc_prev;      // [B, Np, C] merged message of the coarser levels, or NULL (cascade)
     float *out;                 // [B, h0*w0, C] raster: acc_prev[parent] + w * message
@@ -70,7 +73,16 @@ int launch_quad_attention(const FineParams &p, cudaStream_t stream);
 
 // ---- cascade_tile.cu: TMA-tiled CascadeQTAttB (k = 25, dilated = 1); cells it cannot serve go to fb_list
 size_t cascade_tile_smem_bytes();
-int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const float *rel_pos,
+// top-left corner of the win x win window centred on `centre`, shifted rigidly inside [0, n)
+// (CascadeFeatureTransformer.get_window_warp_idx, src/model/modules/transformer.py:427-434)
+__host__ __device__ inline int window_origin(int centre, int win, int n) {
+    int o = centre - win / 2;
+    if (o < 0) o = 0;
+    if (o + win > n) o = n - win;
+    return o;
+}
+int launch_window_idx(const int64_t *next_idx, int64_t *pos, size_t rows, int H, int W, int win, cudaStream_t stream);
+int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const int64_t *next_idx, const float *rel_pos,
                             float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
                             int B, int nh, int h0, int w0, int h1, int w1, cudaStream_t stream);
 

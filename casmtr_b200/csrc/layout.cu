@@ -202,6 +202,29 @@ int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) 
     return CASMTR_OK;
 }
 
+// get_window_warp_idx (src/model/modules/transformer.py:416-440): next_idx [rows] on an H x W grid -> (row, col) of the
+// win x win window around it, shifted rigidly inside the grid: pos [rows, win*win, 2] int64.
+__global__ void window_idx_kernel(const int64_t *__restrict__ next_idx, int64_t *__restrict__ pos, size_t rows, int H, int W, int win) {
+    pdl_sync();
+    const int ww = win * win;
+    const size_t total = rows * ww;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = o / ww;
+        const int k = (int)(o - r * ww);
+        const long long idx = next_idx[r];
+        const int r0 = window_origin((int)(idx / W), win, H), c0 = window_origin((int)(idx % W), win, W);
+        reinterpret_cast<longlong2 *>(pos)[o] = make_longlong2(r0 + k / win, c0 + k % win);
+    }
+}
+
+int launch_window_idx(const int64_t *next_idx, int64_t *pos, size_t rows, int H, int W, int win, cudaStream_t stream) {
+    if (rows == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
+    launch_k(window_idx_kernel, (unsigned)std::min<size_t>((rows * win * win + 255) / 256, 148 * 8), 256, 0, stream, next_idx, pos, rows, H, W, win);
+    CASMTR_CHECK_LAUNCH("window_idx_kernel");
+    return CASMTR_OK;
+}
+
 // internal [B,L,nh,k] int32 / fp32  ->  reference [B,L,k,nh] int64 / fp32
 __global__ void topk_to_api_kernel(const int *__restrict__ idx, const float *__restrict__ score,
                                    int64_t *__restrict__ idx_out, float *__restrict__ score_out,

@@ -103,8 +103,15 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     float pscore = 0.f;
     if (lane < kp) {
         if (CASCADE) {
-            const int64_t *tp = p.topk_pos + (((size_t)b * Np + parent) * kp + lane) * 2;
-            base = (int)(2 * tp[0] * p.w1 + 2 * tp[1]);
+            if (p.next_idx != nullptr) {             // window derived from the parent's match on the previous grid
+                const int hv = p.h1 >> 1, wv = p.w1 >> 1;
+                const int idx = (int)__ldg(p.next_idx + (size_t)b * Np + parent);
+                const int r0 = window_origin(idx / wv, p.win, hv), c0 = window_origin(idx % wv, p.win, wv);
+                base = 2 * (r0 + lane / p.win) * p.w1 + 2 * (c0 + lane % p.win);
+            } else {
+                const int64_t *tp = p.topk_pos + (((size_t)b * Np + parent) * kp + lane) * 2;
+                base = (int)(2 * tp[0] * p.w1 + 2 * tp[1]);
+            }
         } else {
             const size_t o = (((size_t)b * Np + parent) * p.nh + h) * kp + lane;
             const int idx = p.prev_idx[o];
@@ -696,7 +703,7 @@ int launch_list_t(const FineParams &p, cudaStream_t stream) {
 
 template <int KP, int R>
 int launch_by_flags(const FineParams &p, cudaStream_t stream) {
-    if (p.topk_pos) return launch_t<KP, R, true, false, false>(p, stream);       // cascade (gather path): warp per item
+    if (p.topk_pos || p.next_idx) return launch_t<KP, R, true, false, false>(p, stream);       // cascade (gather path): warp per item
     // QTAtt fine levels.  Intermediate levels (top-k, few items, long per-item chain): CTA per item, 4 warps = 4 siblings.
     // Last level (4x the items, no top-k): warp per item -- the CTA variant re-reads the K slab once per sibling warp and
     // becomes shared-memory-pipe bound there (ncu: l1tex 85 %), measured 69 us vs 64 us at 832^2.
@@ -711,7 +718,7 @@ int launch_quad_attention(const FineParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE(p.kp >= 1 && p.kp <= 32, CASMTR_E_UNSUPPORTED, "parent candidate count %d must be in [1,32]", p.kp);
     CASMTR_REQUIRE((p.h0 % 2) == 0 && (p.w0 % 2) == 0, CASMTR_E_INVALID, "query grid %dx%d must be even", p.h0, p.w0);
     if (p.item_list) {                               // cascade fallback cells of the tile kernel
-        CASMTR_REQUIRE(p.topk_pos && p.kp == 25, CASMTR_E_INVALID, "item lists are a cascade (k = 25) feature");
+        CASMTR_REQUIRE((p.topk_pos || p.next_idx) && p.kp == 25, CASMTR_E_INVALID, "item lists are a cascade (k = 25) feature");
         return launch_list_t<25, 4>(p, stream);
     }
     if (p.topk_idx) CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= 4 * p.kp, CASMTR_E_INVALID, "top-k %d must be in [1, min(32, %d)]", p.topk, 4 * p.kp);

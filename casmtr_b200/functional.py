@@ -211,11 +211,25 @@ def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn
     return out
 
 
-def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True, hw_q=None, hw_k=None):
+def window_warp_idx(next_idx, H, W, window=5):
+    """next_idx [B,L] int64 on an H x W grid -> [B,L,window^2,2] (row, col) of the border-shifted window around each match
+    (CascadeFeatureTransformer.get_window_warp_idx, reference transformer.py:416-440)."""
+    _chk(next_idx, 'next_idx', torch.int64)
+    B, L = next_idx.shape
+    pos = torch.empty(B, L, window * window, 2, dtype=torch.int64, device=next_idx.device)
+    with torch.cuda.device(next_idx.device):
+        check(lib().casmtr_window_idx_fwd(_ptr(next_idx), _ptr(pos), B, L, int(H), int(W), int(window), _stream(next_idx)), 'casmtr_window_idx_fwd')
+    return pos
+
+
+def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True, hw_q=None, hw_k=None, window=5):
     """Fused CascadeQTAttB forward -> (message [B,h0*w0,C], upsampled_idx [B,h0*w0,4k] int64 or None).
-    query / key / value: NCHW maps, or - with hw_q / hw_k given - token-major [B, h*w, C] (no transposes)."""
+    query / key / value: NCHW maps, or - with hw_q / hw_k given - token-major [B, h*w, C] (no transposes).
+    topk_pos: [B,(h0/2)*(w0/2),k,2] window positions, or the 2-D next_idx [B,(h0/2)*(w0/2)] they are derived from
+    (the window x window expansion then happens inside the kernels; dilated must be 1)."""
     _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(value, 'value', torch.float32)
     _chk(topk_pos, 'topk_pos', torch.int64)
+    from_idx = topk_pos.dim() == 2
     tokens = hw_q is not None
     if tokens:
         (h0, w0), (h1, w1) = hw_q, hw_k if hw_k is not None else hw_q
@@ -225,8 +239,11 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
     else:
         B, Cc, h0, w0 = query.shape
         h1, w1 = key.shape[2:]
-    k = topk_pos.shape[2]
-    if topk_pos.shape != (B, (h0 // 2) * (w0 // 2), k, 2):
+    k = window * window if from_idx else topk_pos.shape[2]
+    if from_idx:
+        if topk_pos.shape != (B, (h0 // 2) * (w0 // 2)) or (dilated or 1) != 1:
+            raise RuntimeError(f'next_idx must be [B,(h0/2)*(w0/2)] (got {tuple(topk_pos.shape)}) and dilated 1')
+    elif topk_pos.shape != (B, (h0 // 2) * (w0 // 2), k, 2):
         raise RuntimeError(f'topk_pos must be [B,(h0/2)*(w0/2),k,2], got {tuple(topk_pos.shape)}')
     if rel_pos is not None:
         rel_pos = _chk(rel_pos.to(torch.float32).contiguous(), 'rel_pos', torch.float32)
@@ -238,6 +255,11 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
     with torch.cuda.device(dev):
         nbytes = lib().casmtr_cascade_qtatt_workspace_bytes(B, Cc, h0, w0, h1, w1)
         ws = _workspace(nbytes, dev)
+        if from_idx:
+            check(lib().casmtr_cascade_qtatt_window_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), int(window), _ptr(rel_pos), _ptr(msg), _ptr(up),
+                                                        B, nhead, Cc // nhead, h0, w0, h1, w1, 1 if tokens else 0,
+                                                        _ptr(ws), ws.numel(), _stream(msg)), 'casmtr_cascade_qtatt_window_fwd')
+            return msg, up
         fn = lib().casmtr_cascade_qtatt_tokens_fwd if tokens else lib().casmtr_cascade_qtatt_fwd
         check(fn(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), _ptr(rel_pos), _ptr(msg), _ptr(up),
                  B, nhead, Cc // nhead, h0, w0, h1, w1, k, 1 if dilated is None else int(dilated),

@@ -97,6 +97,8 @@ class CascadeQTAttB(nn.Module):
 
     def forward(self, query, key, value, topk_pos, rel_pos):
         """query [N,C,h0,w0], key/value [N,C,h1,w1], topk_pos [N,(h0/2*w0/2),k,2] (row,col), rel_pos None or
-        [N,nhead,h0*w0,4k] -> (message [N,h0*w0,C], upsampled_idx [N,h0*w0,4k] int64)"""
+        [N,nhead,h0*w0,4k] -> (message [N,h0*w0,C], upsampled_idx [N,h0*w0,4k] int64).
+        Extension: topk_pos may be the 2-D next_idx [N,(h0/2*w0/2)] of the previous stage; the 5x5 window expansion
+        (reference transformer.py:416-440) then happens inside the kernel."""
         return F.cascade_qtatt_forward(_f32c(query), _f32c(key), _f32c(value), topk_pos.to(torch.int64).contiguous(),
                                        rel_pos, self.nhead, self.dilated)

@@ -181,6 +181,22 @@ CASMTR_API int casmtr_cascade_qtatt_tokens_fwd(const float *query, const float *
                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
                              void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* Window-index plumbing between the stages (SURVEY 8f "next" #3; src/model/modules/transformer.py:416-440,
+ * CascadeFeatureTransformer.get_window_warp_idx): next_idx [B,L] int64 on an H x W grid -> pos [B,L,window*window,2] int64
+ * (row, col) of the window around each match, shifted rigidly inside the grid.  window odd, <= min(H, W). */
+CASMTR_API int casmtr_window_idx_fwd(const int64_t *next_idx, int64_t *pos, int B, int L, int H, int W, int window,
+                          casmtr_stream_t stream);
+
+/* The fusion of the two: CascadeQTAttB fed with next_idx [B,(h0/2)*(w0/2)] int64 (each parent cell's match on the (h1/2 x w1/2)
+ * grid) instead of the expanded topk_pos; the window is derived inside the kernels, so the [B,L/4,25,2] tensor never exists
+ * and upsampled_idx (optional) is the only index tensor written.  query/key/value NCHW (token_major = 0) or token-major
+ * [B,h*w,C] (token_major = 1).  window in {1,3,5}.  Workspace as casmtr_cascade_qtatt_workspace_bytes. */
+CASMTR_API int casmtr_cascade_qtatt_window_fwd(const float *query, const float *key, const float *value,
+                             const int64_t *next_idx, int window, const float *rel_pos,
+                             float *message, int64_t *upsampled_idx,
+                             int B, int nhead, int D, int h0, int w0, int h1, int w1, int token_major,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- fused cascade matching (R6) */
 
 /* feat0 [B,L0,C], feat1 [B,L1,C] (un-normalised; the 1/sqrt(C) of reference :88 is applied inside);

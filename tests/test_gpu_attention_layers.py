@@ -97,3 +97,32 @@ def test_cascade_quadtree_attention_layer(dev):
         want = layer.proj(msg.view(B, -1, C))
     assert torch.equal(up, up_want)                                  # integer work: bit-exact
     assert (got - want).abs().max() < 1e-3
+
+
+# ---- SURVEY section 8f "next" #3: window-index plumbing
+def test_window_idx_vs_reference(dev):
+    """casmtr_window_idx_fwd against the output of the reference's get_window_warp_idx (tests/golden/windows.npz)."""
+    from golden_util import load
+    g = load('windows')
+    H, W = g['hw'].tolist()
+    pos = F.window_warp_idx(g['idx'].to(dev), H, W, 5)
+    assert torch.equal(pos.cpu(), g['pos'])
+
+
+@pytest.mark.parametrize('B,nh,h,w,tokens', [(1, 4, 64, 64, False), (2, 2, 48, 80, True), (1, 4, 208, 208, False)])
+def test_cascade_from_next_idx(dev, B, nh, h, w, tokens):
+    """Fused window expansion: CascadeQTAttB fed with next_idx == fed with the expanded topk_pos, bit for bit."""
+    C = nh * 32
+    d = synth.cascade_inputs(B, C, h, w, seed=41)
+    v = torch.randn(B, C, h, w, generator=torch.Generator().manual_seed(3))
+    q, k, v = d['feat0'].to(dev), d['feat1'].to(dev), v.to(dev)
+    tp, ni = d['topk_pos01'].to(dev), d['next_idx01'].to(dev)
+    assert torch.equal(F.window_warp_idx(ni, h // 2, w // 2, 5), tp)
+    att = casmtr_b200.CascadeQTAttB(nh, 32, dilated=1)
+    want, up_want = att(q, k, v, tp, None)
+    if tokens:
+        tk = lambda x: x.flatten(2).transpose(1, 2).contiguous()
+        got, up = F.cascade_qtatt_forward(tk(q), tk(k), tk(v), ni, None, nh, hw_q=(h, w), hw_k=(h, w))
+    else:
+        got, up = att(q, k, v, ni, None)
+    assert torch.equal(up, up_want) and torch.equal(got, want)
