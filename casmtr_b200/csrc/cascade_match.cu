@@ -172,7 +172,15 @@ __device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
 }
 
-__host__ __device__ inline int cell_slab_floats(int K, int C) { return (K + 4) * C; }
+// per-warp staging: CSTAGES buffers of a 32-channel (128-byte) slice of the K candidate rows + the 4 query rows.
+// Measured on the fallback list of the 832^2 workload (2164 cells): 1 buffer (13 KB per warp, 16 warps per SM) 34 us,
+// 2 buffers with prefetch (27 KB, 8 warps per SM) 48 us, whole rows (53 KB, 4 warps per SM) 79 us -- cells in flight win.
+constexpr int SLICE = 32;
+#ifndef MATCH_CELL_STAGES
+#define MATCH_CELL_STAGES 1
+#endif
+constexpr int CSTAGES = MATCH_CELL_STAGES;
+__host__ __device__ inline int cell_slab_floats(int K, int C) { (void)C; return CSTAGES * (K + 4) * SLICE; }
 
 template <int CH>
 __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, size_t cell, int lane);
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(256) cascade_match_cell_kernel(MatchParams p, 
 
 template <int CH>
 __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, size_t cell, int lane) {
-    constexpr int C = 4 * CH, RPI = 32 / CH;      // rows per cp.async instruction
+    constexpr int C = 4 * CH;
     constexpr int R = MAX_CHUNKS / 4;             // candidate rounds of 32
     const size_t cells0 = (size_t)p.B * (p.L0 >> 2);
     const bool rev = cell >= cells0;
@@ -235,28 +243,30 @@ __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, si
         return;
     }
 
-    float *Ks = slab;                                            // [K][C], 16-byte chunks XOR-swizzled by (row & 7)
-    float *Qs = Ks + (size_t)K * C;                              // [4][C]
+    // The rows are streamed as NS slices of 32 channels (128 bytes of every candidate row), so a warp needs 13 KB instead
+    // of 53 KB of shared memory (C = 128) -- that is what bounds the number of cells in flight per SM.
+    constexpr int NS = C / SLICE;
+    const int stage_floats = (K + 4) * SLICE;
     const float *kb = d.kf + b * (size_t)d.Lk * C;
-    {   // stage the 4 query rows and the K candidate rows (every global read is a full coalesced row)
-        const int sub = lane / CH, ch = lane % CH;
-#pragma unroll
-        for (int f = sub; f < 4; f += RPI) cp_async16(Qs + f * C + 4 * ch, d.qf + ROWQ(f) * C + 4 * ch);
+    const int sub = lane >> 3, ch = lane & 7;     // a cp.async instruction moves the slice of 4 rows
+    auto stage = [&](int s) {
+        float *Ks = slab + (s % CSTAGES) * stage_floats;         // [K][32], 16-byte chunks XOR-swizzled by (row & 7)
+        float *Qs = Ks + (size_t)K * SLICE;                      // [4][32]
+        cp_async16(Qs + sub * SLICE + 4 * ch, d.qf + ROWQ(sub) * C + s * SLICE + 4 * ch);
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             if (32 * m < K) {
-#pragma unroll 4
-                for (int l = 0; l < 32; l += RPI) {
+#pragma unroll
+                for (int l = 0; l < 32; l += 4) {
                     const int ci = __shfl_sync(FULL_MASK, cand[m], l + sub);
                     const int k = 32 * m + l + sub;
-                    if (k < K) cp_async16(Ks + (size_t)k * C + 4 * (ch ^ (k & 7)), kb + (size_t)ci * C + 4 * ch);
+                    if (k < K) cp_async16(Ks + (size_t)k * SLICE + 4 * (ch ^ (k & 7)), kb + (size_t)ci * C + s * SLICE + 4 * ch);
                 }
             }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncwarp();
-    }
+    };
+    stage(0);
 
     // correlation: lane = candidate 32r + lane; q chunks are broadcast reads shared by the rounds
     float sc[R][4];
@@ -264,27 +274,41 @@ __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, si
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int f = 0; f < 4; ++f) sc[r][f] = 0.f;
-    const float *krow[R];
-    int sw[R];
+    int koff[R], sw[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int c = min(32 * r + lane, K - 1);  // rows past K re-read the last row; masked below
-        krow[r] = Ks + (size_t)c * C;
+        koff[r] = c * SLICE;
         sw[r] = c & 7;
     }
-#pragma unroll 2
-    for (int j = 0; j < CH; ++j) {
-        float4 qv[4];
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) {
+        if (CSTAGES == 1) {
+            if (s > 0) stage(s);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        } else if (s + 1 < NS) {
+            stage(s + 1);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncwarp();
+        const float *Ks = slab + (s % CSTAGES) * stage_floats, *Qs = Ks + (size_t)K * SLICE;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + f * C + 4 * j);
+        for (int j = 0; j < SLICE / 4; ++j) {
+            float4 qv[4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (32 * r < K) {                     // warp-uniform
-                const float4 kv = *reinterpret_cast<const float4 *>(krow[r] + 4 * (j ^ sw[r]));
+            for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + f * SLICE + 4 * j);
 #pragma unroll
-                for (int f = 0; f < 4; ++f) sc[r][f] = dot4acc(qv[f], kv, sc[r][f]);
+            for (int r = 0; r < R; ++r) {
+                if (32 * r < K) {                 // warp-uniform
+                    const float4 kv = *reinterpret_cast<const float4 *>(Ks + koff[r] + 4 * (j ^ sw[r]));
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) sc[r][f] = dot4acc(qv[f], kv, sc[r][f]);
+                }
             }
         }
+        __syncwarp();                             // the stage is rewritten two slices later
     }
     // scale, window mask (:108-112, :125)
     bool q_ok[4] = {true, true, true, true};
@@ -355,7 +379,7 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
     LaunchScope ls(listed ? CASMTR_K_CASCADE_FALLBACK : CASMTR_K_CASCADE_MATCH, stream);
     if (quad) {
         const size_t per_warp = sizeof(float) * cell_slab_floats(p.K, p.C);
-        int wpc = (int)((113 * 1024) / per_warp);
+        int wpc = (int)((110 * 1024) / per_warp);               // two CTAs per SM
         wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
         const size_t smem = per_warp * wpc;
         const unsigned blocks = listed ? 2 * 148 : (unsigned)((rows / 4 + wpc - 1) / wpc);

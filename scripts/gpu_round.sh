@@ -20,7 +20,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|qtatt_coarse|quad_cta|quad_attention_kernel' -c 4 -f -o $OUT/${TAG}_qtatt $BENCH > $OUT/${TAG}_ncu_a.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|cascade_att_tile|quad_attention_list' -s 12 -c 3 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_match|extract_|fine_match' -c 6 -f -o $OUT/${TAG}_match $BENCH > $OUT/${TAG}_ncu_c.log 2>&1
-for r in qtatt cascade match; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'coarse_rowstats|pool2_tokens|fine_window_gather|tf32_residual' -c 4 -f -o $OUT/${TAG}_widen $BENCH > $OUT/${TAG}_ncu_d.log 2>&1
+for r in qtatt cascade match widen; do
   ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null
 done
 ls -la $OUT; du -sh $OUT
