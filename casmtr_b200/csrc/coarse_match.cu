@@ -84,7 +84,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_constant__ CoarseMaps maps, CoarseStatParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 128B-swizzled TMA tiles want 1024-byte alignment; an offset
+                                                                                 // on the __shared__ pointer (not an integer round trip) keeps LDS/STS
     uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + NSTG, *tfull = empty + NSTG, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 

@@ -41,7 +41,8 @@ struct Maps { CUtensorMap key[2], qry[2]; };              // [direction]: key im
 __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel(const __grid_constant__ Maps maps, MatchParams p) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 128B-swizzled TMA tiles want 1024-byte alignment; an offset
+                                                                                 // on the __shared__ pointer (not an integer round trip) keeps LDS/STS
     uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + NSTAGE;
     CellMeta *meta = (CellMeta *)(sm + SM_META);
 

@@ -1,8 +1,8 @@
-timeout 900 python -m pytest tests/test_gpu_matching.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/r01y_bench.json 2> gpurun_out/r01y_bench.err; echo "bench exit $?"
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/r01y_bench.json').read().strip().splitlines()[-1])
-print('value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'eager', round(d['ms_per_step_eager_instrumented'],4))
+print('value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'eager', round(d['ms_per_step_eager_instrumented'],4), 'coarse_match', d['next_rows']['coarse_matching']['ms_per_call'])
 for b in d['breakdown']: print(b['kind'], b['launches_per_step'], b['ms_per_launch'], b['share'])
 PY
