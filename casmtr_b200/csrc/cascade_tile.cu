@@ -48,7 +48,9 @@ struct CellMeta { int flag, wy0, wx0, r0, c0; };   // flag: 1 = compute from the
 constexpr int NCONS = TP * TP;                       // consumer warps = cells per tile
 constexpr int Q_BYTES = (2 * TP) * (2 * TP) * D * 4; // the block's 8x8 query tokens of one head
 constexpr int STAGE_BYTES = 2 * TILE_BYTES + Q_BYTES;
+struct WorkMeta { int h, b, ty, tx; };              // the work item of a stage, decoded once by the producer
 constexpr int SM_META = 2 * STAGE_BYTES;                              // CellMeta[2][NCONS]
+constexpr int SM_WORK = SM_META + 2 * NCONS * (int)sizeof(CellMeta);  // WorkMeta[2] (inside the 64 bytes of slack below)
 constexpr int SM_A = SM_META + 2 * NCONS * (int)sizeof(CellMeta) + 64; // float[NCONS][100][4], 16-byte aligned below
 constexpr int SM_BAR = ((SM_A + 15) / 16) * 16 + NCONS * KC * 4 * 4;  // uint64 full[2], empty[2]
 constexpr int SM_TOTAL = SM_BAR + 4 * 8;
@@ -62,6 +64,7 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                                                                                  // on the __shared__ pointer (not an integer round trip) keeps LDS/STS
     uint64_t *full = (uint64_t *)(sm + SM_BAR), *empty = full + 2;
     CellMeta *meta = (CellMeta *)(sm + SM_META);
+    WorkMeta *work = (WorkMeta *)(sm + SM_WORK);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hp = p.h0 >> 1, wp = p.w0 >> 1, Np = hp * wp;
@@ -139,6 +142,7 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 m.flag = use_tile; m.wy0 = wy0; m.wx0 = wx0; m.r0 = r0; m.c0 = c0;
                 meta[s * NCONS + lane] = m;
             }
+            if (lane == 0) work[s] = WorkMeta{h, b, ty, tx};
             __syncwarp();
             if (lane == 0) {
                 uint8_t *st = sm + s * STAGE_BYTES;
@@ -159,15 +163,15 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int s = it & 1;
-        const int h = w % p.nh, tile = (w / p.nh) % n_tiles, b = w / (p.nh * n_tiles);
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const float *Kt = (const float *)(sm + s * STAGE_BYTES);              // [TH*TW][32], 16-byte chunk c of row r at chunk c ^ (r & 7)
         const float *Vt = (const float *)(sm + s * STAGE_BYTES + TILE_BYTES);
         const float *Qt = (const float *)(sm + s * STAGE_BYTES + 2 * TILE_BYTES);  // [8][8][32] query tokens of the block, unswizzled
         mbar_wait(full + s, (it >> 1) & 1);
         const CellMeta m = meta[s * NCONS + warp];
         if (m.flag) {
-            const int py = ty * TP + ly, px = tx * TP + lx;
+            const WorkMeta wm = work[s];
+            const int h = wm.h, b = wm.b;
+            const int py = wm.ty * TP + ly, px = wm.tx * TP + lx;
             const int qtok0 = 2 * py * p.w0 + 2 * px;
 #define QTOK(f) (qtok0 + ((f) >> 1) * p.w0 + ((f) & 1))
             const float *Qs = Qt + ((2 * ly) * (2 * TP) + 2 * lx) * D;        // sibling f at + ((f>>1) * 8 + (f&1)) * 32
@@ -211,10 +215,17 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 const int c = 32 * r + lane;
                 const bool valid = c < KC;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    float sv = sc[r][f] * scale;
-                    if (p.rel_pos != nullptr && valid) sv += __ldg(p.rel_pos + (((size_t)b * p.nh + h) * L0 + QTOK(f)) * KC + c);
-                    sc[r][f] = valid ? sv : -INFINITY;
+                for (int f = 0; f < 4; ++f) sc[r][f] = valid ? sc[r][f] * scale : -INFINITY;
+            }
+            if (p.rel_pos != nullptr) {                       // relative position bias (indoor configuration only)
+                const float *rp = p.rel_pos + ((size_t)b * p.nh + h) * L0 * KC;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int c = 32 * r + lane;
+                    if (c < KC) {
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) sc[r][f] += __ldg(rp + (size_t)QTOK(f) * KC + c);
+                    }
                 }
             }
             // ---- softmax over the 100 candidates per sibling

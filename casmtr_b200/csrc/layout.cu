@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4)
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
+    __builtin_assume(__isGlobal(jb.src) && __isGlobal(jb.dst));
     const int ho = jb.h >> 1, wo = jb.w >> 1;
     const size_t n = (size_t)ho * wo * C4;
     const float4 *src = reinterpret_cast<const float4 *>(jb.src) + (size_t)b * jb.h * jb.w * C4;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) pool2_tokens_kernel(PoolJobs jobs, int C4
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
+    __builtin_assume(__isGlobal(jb.src) && __isGlobal(jb.dst) && __isGlobal(jb.dst2));
     const int h1 = jb.h >> 1, w1 = jb.w >> 1, h2 = jb.h >> 2, w2 = jb.w >> 2;
     const size_t n = (size_t)h2 * w2 * C4;
     const float4 *src = reinterpret_cast<const float4 *>(jb.src) + (size_t)b * jb.h * jb.w * C4;
