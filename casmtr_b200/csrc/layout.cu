@@ -114,7 +114,7 @@ int launch_transpose_jobs(TransposeJobs &jobs, int B, cudaStream_t stream) {
 // 2x2 average pooling of token-major maps [B, h*w, C] -> [B, (h/2)*(w/2), C]: one pyramid level of
 // QuadtreeAttention.forward (src/model/modules/quadtree_attention.py:86-89, F.avg_pool2d(kernel 2, stride 2)); the four
 // taps are summed in avg_pool2d's window order.  Thread = 4 channels of one output token; up to 3 maps (q, k, v) per launch.
-__global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4) {
+__global__ void __launch_bounds__(256) pool_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(PoolJobs jobs, int C4)
 
 // Two pyramid levels in one pass (h, w multiples of 4): thread = 4 channels of one level-2 token; its 4x4 block of level-0
 // tokens is read once, the four level-1 averages are written and averaged again (the reference pools the pooled map).
-__global__ void __launch_bounds__(256) pool2_tokens_kernel(PoolJobs jobs, int C4) {
+__global__ void __launch_bounds__(256) pool2_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
