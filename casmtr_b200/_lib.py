@@ -73,6 +73,10 @@ SIGNATURES = {
                                        c_float_p, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_pack_matches': (C.c_int, [c_i64_p, c_i64_p, c_i64_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_void_p]),
+    'casmtr_pack_matches_dev': (C.c_int, [c_i64_p, c_i64_p, c_i64_p, c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_int64, C.c_int,
+                                          C.c_void_p, C.c_void_p]),
+    'casmtr_fine_match_dev_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_i64_p, C.c_float,
+                                            c_float_p, c_float_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'casmtr_fine_window_gather': (C.c_int, [c_float_p, c_i64_p, c_i64_p, c_float_p] + [C.c_int] * 7 + [C.c_void_p]),
     'casmtr_fine_match_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_i64_p, C.c_float,
                                         c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -501,7 +501,15 @@ int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_
                         unsigned char *out, casmtr_stream_t stream) {
     CASMTR_REQUIRE(M >= 0 && capacity >= M && out != nullptr, CASMTR_E_INVALID, "pack_matches: M=%d capacity=%d", M, capacity);
     CASMTR_REQUIRE(M == 0 || (b_ids && i_ids && j_ids && mconf && mkpts0 && mkpts1), CASMTR_E_INVALID, "pack_matches: null pointer");
-    return launch_pack_matches(b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, M, pair_offset, out, (cudaStream_t)stream);
+    return launch_pack_matches(b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, M, pair_offset, out, nullptr, (cudaStream_t)stream);
+}
+
+int casmtr_pack_matches_dev(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf,
+                            const float *mkpts0, const float *mkpts1, const int32_t *count, int64_t pair_offset, int capacity,
+                            unsigned char *out, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(capacity >= 0 && out && count && b_ids && i_ids && j_ids && mconf && mkpts0 && mkpts1, CASMTR_E_INVALID,
+                   "pack_matches_dev: null pointer or negative capacity");
+    return launch_pack_matches(b_ids, i_ids, j_ids, mconf, mkpts0, mkpts1, capacity, pair_offset, out, count, (cudaStream_t)stream);
 }
 
 int casmtr_fine_window_gather(const float *feat, const int64_t *b_ids, const int64_t *ids, float *out, int M, int C, int Hf, int Wf,
@@ -519,7 +527,16 @@ int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const floa
     CASMTR_REQUIRE(M >= 0 && WW > 0 && C > 0, CASMTR_E_INVALID, "fine_match: bad sizes");
     CASMTR_REQUIRE(M == 0 || (feat_f0 && feat_f1 && mkpts1_c && expec_f && mkpts1_f), CASMTR_E_INVALID, "fine_match: null pointer");
     CASMTR_REQUIRE(scale1_b == nullptr || b_ids != nullptr, CASMTR_E_INVALID, "fine_match: scale1_b needs b_ids");
-    return launch_fine_match(feat_f0, feat_f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, C, (cudaStream_t)stream);
+    return launch_fine_match(feat_f0, feat_f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, C, nullptr, (cudaStream_t)stream);
+}
+
+int casmtr_fine_match_dev_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
+                              const float *scale1_b, const int64_t *b_ids, float scale,
+                              float *expec_f, float *mkpts1_f, const int32_t *count, int capacity, int WW, int C, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(capacity >= 0 && WW > 0 && C > 0 && count, CASMTR_E_INVALID, "fine_match_dev: bad sizes");
+    CASMTR_REQUIRE(capacity == 0 || (feat_f0 && feat_f1 && mkpts1_c && expec_f && mkpts1_f), CASMTR_E_INVALID, "fine_match_dev: null pointer");
+    CASMTR_REQUIRE(scale1_b == nullptr || b_ids != nullptr, CASMTR_E_INVALID, "fine_match_dev: scale1_b needs b_ids");
+    return launch_fine_match(feat_f0, feat_f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, capacity, WW, C, count, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -205,8 +205,10 @@ __global__ void __launch_bounds__(BLK) extract_emit_kernel(ExtractArgs a, EmitOu
 // ---- packed match records for the multi-GPU all-gather: row 0 = count, rows 1..M = 44-byte records
 __global__ void pack_matches_kernel(const int64_t *__restrict__ b_ids, const int64_t *__restrict__ i_ids, const int64_t *__restrict__ j_ids,
                                     const float *__restrict__ mconf, const float *__restrict__ mk0, const float *__restrict__ mk1,
-                                    int M, long long pair_offset, unsigned char *__restrict__ out) {
+                                    int M, long long pair_offset, unsigned char *__restrict__ out, const int32_t *__restrict__ count_dev) {
+    pdl_sync();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (count_dev != nullptr) M = min(M, (int)__ldg(count_dev));      // M is then the capacity, the count is read on the device
     if (r > M) return;
     unsigned *w = reinterpret_cast<unsigned *>(out + (size_t)r * 44);          // 44-byte rows are 4-byte aligned
     if (r == 0) {
@@ -226,9 +228,9 @@ __global__ void pack_matches_kernel(const int64_t *__restrict__ b_ids, const int
 }
 
 int launch_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf, const float *mk0,
-                        const float *mk1, int M, long long pair_offset, unsigned char *out, cudaStream_t stream) {
+                        const float *mk1, int M, long long pair_offset, unsigned char *out, const int32_t *count_dev, cudaStream_t stream) {
     LaunchScope ls(CASMTR_K_EXTRACT, stream);
-    pack_matches_kernel<<<(M + 1 + 255) / 256, 256, 0, stream>>>(b_ids, i_ids, j_ids, mconf, mk0, mk1, M, pair_offset, out);
+    launch_k(pack_matches_kernel, (M + 1 + 255) / 256, 256, 0, stream, b_ids, i_ids, j_ids, mconf, mk0, mk1, M, pair_offset, out, count_dev);
     CASMTR_CHECK_LAUNCH("pack_matches_kernel");
     return CASMTR_OK;
 }

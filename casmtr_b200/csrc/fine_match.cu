@@ -12,10 +12,11 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const float *__restrict
                                                           const float *__restrict__ mkpts1_c, const float *__restrict__ scale1_b,
                                                           const int64_t *__restrict__ b_ids, float scale,
                                                           float *__restrict__ expec_f, float *__restrict__ mkpts1_f,
-                                                          int M, int WW, int W, int C) {
+                                                          int M, int WW, int W, int C, const int32_t *__restrict__ count_dev) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (count_dev != nullptr) M = min(M, (int)__ldg(count_dev));      // match count still on the device (no host sync yet)
     if (m >= M) return;
     const float *centre = f0 + ((size_t)m * WW + WW / 2) * C;          // feat_f0[:, WW//2, :]  (:105)
     float sim = -INFINITY;
@@ -90,14 +91,14 @@ int launch_fine_window_gather(const float *feat, const int64_t *b_ids, const int
 
 int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, const float *scale1_b,
                       const int64_t *b_ids, float scale, float *expec_f, float *mkpts1_f,
-                      int M, int WW, int C, cudaStream_t stream) {
+                      int M, int WW, int C, const int32_t *count_dev, cudaStream_t stream) {
     int W = 1;
     while (W * W < WW) ++W;
     CASMTR_REQUIRE(W * W == WW && WW <= 32 && W >= 2, CASMTR_E_UNSUPPORTED, "fine_match: window %d must be a square <= 32 (W in 2..5)", WW);
     CASMTR_REQUIRE(C % 4 == 0 && C > 0, CASMTR_E_UNSUPPORTED, "fine_match: C=%d must be a positive multiple of 4", C);
     if (M == 0) return CASMTR_OK;
     LaunchScope ls(CASMTR_K_FINE_MATCH, stream);
-    launch_k(fine_match_kernel, (M + 7) / 8, 256, 0, stream, f0, f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, W, C);
+    launch_k(fine_match_kernel, (M + 7) / 8, 256, 0, stream, f0, f1, mkpts1_c, scale1_b, b_ids, scale, expec_f, mkpts1_f, M, WW, W, C, count_dev);
     CASMTR_CHECK_LAUNCH("fine_match_kernel");
     return CASMTR_OK;
 }

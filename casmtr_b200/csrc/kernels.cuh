@@ -128,11 +128,11 @@ int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01,
                          int32_t *count_out, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t match_extract_workspace(const casmtr_extract_desc &d);
 int launch_pack_matches(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf, const float *mk0,
-                        const float *mk1, int M, long long pair_offset, unsigned char *out, cudaStream_t stream);
+                        const float *mk1, int M, long long pair_offset, unsigned char *out, const int32_t *count_dev, cudaStream_t stream);
 
 // ---- fine_match.cu
 int launch_fine_window_gather(const float *feat, const int64_t *b_ids, const int64_t *ids, float *out, int M, int C, int Hf, int Wf,
                               int wc, int stride, int W, cudaStream_t stream);
 int launch_fine_match(const float *f0, const float *f1, const float *mkpts1_c, const float *scale1_b,
                       const int64_t *b_ids, float scale, float *expec_f, float *mkpts1_f,
-                      int M, int WW, int C, cudaStream_t stream);
+                      int M, int WW, int C, const int32_t *count_dev, cudaStream_t stream);

@@ -11,6 +11,39 @@ import torch.distributed as dist
 RECORD_BYTES = 3 * 8 + 5 * 4      # b_id, i_id, j_id (int64) + mconf, mkpts0[2], mkpts1[2] (fp32)
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index, sysfs='/sys'):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated: first
+    touch then places the staging buffers in memory local to the GPU's PCIe root, so the host->device copies of 8 ranks do
+    not all cross the socket interconnect.  Returns {'node': n, 'cpus': count} or None when the topology is not exposed
+    (containers without sysfs, single-node hosts): binding is an optimisation, never a requirement."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f'{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0'
+        with open(f'{sysfs}/bus/pci/devices/{bdf}/numa_node') as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f'{sysfs}/devices/system/node/node{node}/cpulist') as fh:
+            cpus = _parse_cpulist(fh.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {'node': node, 'cpus': len(cpus)}
+    except (OSError, AttributeError, ValueError):
+        return None
+
+
 def shard_range(n_pairs, rank, world):
     """Contiguous split of n_pairs over `world` ranks: rank r gets [lo, hi)."""
     base, rem = divmod(n_pairs, world)
@@ -35,18 +68,21 @@ def unpack_matches(buf):
             'mkpts0': fl[:, 1:3], 'mkpts1': fl[:, 3:5]}
 
 
-def gather_matches_device(m, pair_offset, cap, group=None):
+def gather_matches_device(m, pair_offset, cap, group=None, async_op=False):
     """Stream-ordered variant for CUDA tensors: one pack kernel (libcasmtr_b200) + one fixed-size NCCL all-gather, no host
     synchronisation.  Returns the gathered blocks [world, cap+1, 44] uint8 on the device; unpack_gathered() turns them
-    into the match dict when the host needs it."""
+    into the match dict when the host needs it.
+    async_op: return (blocks, work) and do NOT make the compute stream wait for the collective -- the next pair's kernels
+    do not depend on it, so it overlaps them; call work.wait() before reading the blocks."""
     from . import functional as F
     block = F.pack_matches(m, pair_offset, cap)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return block.unsqueeze(0)
+        return (block.unsqueeze(0), None) if async_op else block.unsqueeze(0)
     allb = torch.empty(world * (cap + 1), RECORD_BYTES, dtype=torch.uint8, device=block.device)
-    dist.all_gather_into_tensor(allb, block, group=group)
-    return allb.reshape(world, cap + 1, RECORD_BYTES)
+    work = dist.all_gather_into_tensor(allb, block, group=group, async_op=async_op)
+    allb = allb.reshape(world, cap + 1, RECORD_BYTES)
+    return (allb, work) if async_op else allb
 
 
 def unpack_gathered(allb):

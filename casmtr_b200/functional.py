@@ -385,17 +385,27 @@ def trim_matches(full):
 
 
 def pack_matches(m, pair_offset, cap):
-    """dict(b_ids,i_ids,j_ids,mconf,mkpts0,mkpts1) of M matches -> uint8 [cap+1, 44] block (row 0 = count), one kernel."""
+    """dict(b_ids,i_ids,j_ids,mconf,mkpts0,mkpts1) of M matches -> uint8 [cap+1, 44] block (row 0 = count), one kernel.
+    If m carries 'count' (int32 device tensor of a deferred extraction) the arrays are capacity-sized and the count is read
+    on the device: no host synchronisation."""
+    count = m.get('count')
     M = int(m['b_ids'].shape[0])
-    if M > cap:
+    if count is not None:
+        cap = min(cap, M)
+    elif M > cap:
         raise RuntimeError(f'pack_matches: {M} matches exceed the static capacity {cap}')
     dev = m['b_ids'].device
     out = torch.empty(cap + 1, 44, dtype=torch.uint8, device=dev)
     t = [_chk(m[k].contiguous(), k, dt) for k, dt in (('b_ids', torch.int64), ('i_ids', torch.int64), ('j_ids', torch.int64),
                                                       ('mconf', torch.float32), ('mkpts0', torch.float32), ('mkpts1', torch.float32))]
     with torch.cuda.device(dev):
-        check(lib().casmtr_pack_matches(*[_ptr(x) for x in t], M, int(pair_offset), int(cap), _ptr(out), _stream(out)),
-              'casmtr_pack_matches')
+        if count is not None:
+            _chk(count, 'count', torch.int32)
+            check(lib().casmtr_pack_matches_dev(*[_ptr(x) for x in t], _ptr(count), int(pair_offset), int(cap), _ptr(out), _stream(out)),
+                  'casmtr_pack_matches_dev')
+        else:
+            check(lib().casmtr_pack_matches(*[_ptr(x) for x in t], M, int(pair_offset), int(cap), _ptr(out), _stream(out)),
+                  'casmtr_pack_matches')
     return out
 
 
@@ -412,8 +422,9 @@ def fine_window_gather(feat, b_ids, ids, wc, stride, W=5):
     return out
 
 
-def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None):
-    """-> (expec_f [M,3], mkpts1_f [M,2])."""
+def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=None, count=None):
+    """-> (expec_f [M,3], mkpts1_f [M,2]).  count: optional int32 device tensor -- only rows [0, count) are computed (the
+    inputs are then capacity-sized buffers of a deferred extraction; rows past the count are left uninitialised)."""
     _chk(feat_f0, 'feat_f0', torch.float32), _chk(feat_f1, 'feat_f1', torch.float32)
     M, WW, Cc = feat_f0.shape
     dev = feat_f0.device
@@ -425,6 +436,11 @@ def fine_match_forward(feat_f0, feat_f1, mkpts1_c, scale, scale1_b=None, b_ids=N
         s1 = _chk(scale1_b.to(torch.float32).contiguous(), 'scale1', torch.float32)
         bi = _chk(b_ids.contiguous(), 'b_ids', torch.int64)
     with torch.cuda.device(dev):
-        check(lib().casmtr_fine_match_fwd(_ptr(feat_f0), _ptr(feat_f1), _ptr(mk), _ptr(s1), _ptr(bi), float(scale),
-                                          _ptr(expec), _ptr(out), M, WW, Cc, _stream(expec)), 'casmtr_fine_match_fwd')
+        if count is not None:
+            _chk(count, 'count', torch.int32)
+            check(lib().casmtr_fine_match_dev_fwd(_ptr(feat_f0), _ptr(feat_f1), _ptr(mk), _ptr(s1), _ptr(bi), float(scale),
+                                                  _ptr(expec), _ptr(out), _ptr(count), M, WW, Cc, _stream(expec)), 'casmtr_fine_match_dev_fwd')
+        else:
+            check(lib().casmtr_fine_match_fwd(_ptr(feat_f0), _ptr(feat_f1), _ptr(mk), _ptr(s1), _ptr(bi), float(scale),
+                                              _ptr(expec), _ptr(out), M, WW, Cc, _stream(expec)), 'casmtr_fine_match_fwd')
     return expec, out

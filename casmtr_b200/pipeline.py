@@ -163,6 +163,17 @@ class HotPath(nn.Module):
         return {'b_ids': st['b_ids'], 'i_ids': st['i_ids'], 'j_ids': st['j_ids'], 'mconf': st['mconf'],
                 'mkpts0': data['mkpts0_f'], 'mkpts1': data['mkpts1_f'], 'expec_f': data['expec_f']}
 
+    def run_fine_deferred(self, data, fine_in):
+        """Fine stage on the capacity-sized buffers of a defer_sync extraction: the match count stays on the device (the
+        fine kernel reads it there), so nothing in the step waits for the host.  Returns capacity-sized arrays + 'count';
+        trim_result() slices them once the host may read the count."""
+        d = data['stage_4c']['_deferred']
+        cap = min(d['b_ids'].shape[0], fine_in['feat_f0'].shape[0])
+        scale = data['hw0_i'][0] / data['hw0_f'][0]
+        expec, mk1 = F.fine_match_forward(fine_in['feat_f0'][:cap], fine_in['feat_f1'][:cap], d['mkpts1_c'][:cap], scale, count=d['count'])
+        return {'b_ids': d['b_ids'][:cap], 'i_ids': d['i_ids'][:cap], 'j_ids': d['j_ids'][:cap], 'mconf': d['mconf'][:cap],
+                'mkpts0': d['mkpts0_c'][:cap], 'mkpts1': mk1, 'expec_f': expec, 'count': d['count']}
+
     @torch.no_grad()
     def forward(self, dev_in, keep=None):
         """dev_in: make_host_inputs() moved to the GPU.  Returns the match list dict.  `keep`, if a dict, receives
@@ -185,14 +196,24 @@ class HotPath(nn.Module):
         return out
 
 
+def trim_result(out):
+    """Capacity-sized result of a sync-free step -> the match list (reads the device-side count: the one host sync)."""
+    if 'count' not in out:
+        return out
+    M = min(int(out['count'].item()), out['b_ids'].shape[0])
+    return {k: v[:M] for k, v in out.items() if k != 'count'}
+
+
 class GraphRunner:
     """CUDA-graph replay of a step with the model's own concurrency: the two directions of a layer (calls 2i, 2i+1:
     feat0->feat1 and feat1->feat0, computed from the same inputs in the reference, src/model/modules/transformer.py:300)
-    run on two streams forked/joined inside the graph.  The graph ends before the one host sync of the path (the match
-    count); the fine stage runs eagerly after it.  Inputs are the static device buffers given at capture time."""
+    run on two streams forked/joined inside the graph.  Inputs are the static device buffers given at capture time.
+    whole_step=False: the graph ends before the one host sync of the path (the match count); the fine stage runs eagerly
+    after it.  whole_step=True: the fine stage is captured too, reading the match count on the device -- a step is ONE graph
+    launch without any host synchronisation and returns capacity-sized buffers + 'count' (see trim_result)."""
 
-    def __init__(self, hp, dev_in, two_streams=True):
-        self.hp, self.dev_in = hp, dev_in
+    def __init__(self, hp, dev_in, two_streams=True, whole_step=False):
+        self.hp, self.dev_in, self.whole_step = hp, dev_in, whole_step
         dev = dev_in['match']['feat0'].device
         hp.matching.defer_sync = True
         try:
@@ -238,10 +259,14 @@ class GraphRunner:
         for i, (_, up) in enumerate(cas):
             idx[i % 2] = up
         self.data = hp.run_match(d, idx[0], idx[1])
+        if self.whole_step:
+            self.out = hp.run_fine_deferred(self.data, d['fine'])
 
     @torch.no_grad()
     def step(self):
         self.graph.replay()
+        if self.whole_step:
+            return self.out                         # static buffers, rewritten by every replay
         self.data['stage_4c']['_deferred'] = self.deferred
         self.hp.matching.finalize(self.data)        # host sync: the match count
         return self.hp.run_fine(self.data, self.dev_in['fine'])

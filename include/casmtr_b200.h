@@ -271,6 +271,12 @@ CASMTR_API int casmtr_pack_matches(const int64_t *b_ids, const int64_t *i_ids, c
                         const float *mkpts0, const float *mkpts1, int M, int64_t pair_offset, int capacity,
                         unsigned char *out, casmtr_stream_t stream);
 
+/* Same with the match count still on the device (count = the int32 casmtr_match_extract wrote; the arrays hold `capacity`
+ * rows): min(*count, capacity) records are packed, no host synchronisation between extraction and the all-gather. */
+CASMTR_API int casmtr_pack_matches_dev(const int64_t *b_ids, const int64_t *i_ids, const int64_t *j_ids, const float *mconf,
+                        const float *mkpts0, const float *mkpts1, const int32_t *count, int64_t pair_offset, int capacity,
+                        unsigned char *out, casmtr_stream_t stream);
+
 /* Window gather of CascadeFinePreprocess (src/model/functions/fine_matching.py:47-55; SURVEY 8f "next" #4): for match m the
  * W x W window of the fine map feat [B,C,Hf,Wf] centred on coarse token ids[m] (grid width wc, fine = coarse * stride),
  * zero padded, written as out [M, W*W, C].  Equals F.unfold(feat, W, stride=stride, padding=W/2)[b_ids, ids] of the reference
@@ -285,6 +291,13 @@ CASMTR_API int casmtr_fine_window_gather(const float *feat, const int64_t *b_ids
 CASMTR_API int casmtr_fine_match_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
                           const float *scale1_b, const int64_t *b_ids, float scale,
                           float *expec_f, float *mkpts1_f, int M, int WW, int C, casmtr_stream_t stream);
+
+/* Same with the match count on the device: rows [0, min(*count, capacity)) are computed, the rest of the outputs is left
+ * untouched -- lets the whole path (extraction -> fine matching) run without the host reading the count in between. */
+CASMTR_API int casmtr_fine_match_dev_fwd(const float *feat_f0, const float *feat_f1, const float *mkpts1_c,
+                          const float *scale1_b, const int64_t *b_ids, float scale,
+                          float *expec_f, float *mkpts1_f, const int32_t *count, int capacity, int WW, int C,
+                          casmtr_stream_t stream);
 
 #ifdef __cplusplus
 }

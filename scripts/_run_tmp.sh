@@ -1,4 +1,8 @@
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests -m gpu -x -q -k "not 10816" > gpurun_out/r01z_memcheck.log 2>&1; echo "memcheck exit $?"
-tail -6 gpurun_out/r01z_memcheck.log
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_qtatt.py tests/test_gpu_matching.py tests/test_gpu_golden.py -m gpu -x -q -k "not 104 and not 208" > gpurun_out/r01z_racecheck.log 2>&1; echo "racecheck exit $?"
-tail -30 gpurun_out/r01z_racecheck.log | cut -c1-220
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r01y_bench.json 2> gpurun_out/r01y_bench.err; echo "bench exit $?"
+tail -3 gpurun_out/r01y_bench.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r01y_bench.json').read().strip().splitlines()[-1])
+print('value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'eager', round(d['ms_per_step_eager_instrumented'],4), d['execution'], d['cuda_graph'], d['e2e'])
+PY

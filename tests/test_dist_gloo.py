@@ -67,3 +67,9 @@ def test_gather_matches_world2():
         assert a[k] == b[k]
     assert a['b_ids'] == want['b_ids'].tolist() and a['mkpts0'] == want['mkpts0'].tolist()
     assert len(a['b_ids']) == 11
+
+
+def test_cpulist_parse():
+    from casmtr_b200.dist import _parse_cpulist
+    assert _parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist('') == set()

@@ -110,3 +110,23 @@ def test_match_list_properties(run, dev):
     assert out['mkpts1'].shape == (M, 2) and out['expec_f'].shape == (M, 3)
     e, k = ofine.fine_match(host['fine']['feat_f0'][:M], host['fine']['feat_f1'][:M], st['mkpts1_c'].cpu(), wl.H / wl.hf)
     assert (out['expec_f'].cpu() - e).abs().max() < 1e-5 and (out['mkpts1'].cpu() - k).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('two_streams', [False, True])
+def test_whole_step_graph_equals_eager(run, dev, two_streams):
+    """The sync-free CUDA-graph step (match count consumed on the device by the fine stage) returns exactly the eager
+    result once trimmed; replaying it is idempotent."""
+    wl, host, hp, dev_in, keep, out = run
+    gr = pipeline.GraphRunner(hp, dev_in, two_streams=two_streams, whole_step=True)
+    for _ in range(2):
+        got = pipeline.trim_result(gr.step())
+        torch.cuda.synchronize()
+        assert got['mconf'].shape[0] == out['mconf'].shape[0] > 100
+        for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0', 'mkpts1', 'expec_f'):
+            assert torch.equal(got[k], out[k]), k
+    # the packed all-gather block built from the device-side count equals the one built from the trimmed list
+    from casmtr_b200 import functional as F
+    blk_dev = F.pack_matches(gr.step(), 7, wl.fine_cap)
+    blk = F.pack_matches({k: out[k] for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0', 'mkpts1')}, 7, wl.fine_cap)
+    M = out['mconf'].shape[0]
+    assert torch.equal(blk_dev[:M + 1], blk[:M + 1])
