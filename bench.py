@@ -354,6 +354,29 @@ def run_ours(args):
         e2e = {'value': wl.B * n_gpus / (e_ms / args.steps / 1000.0), 'unit': UNIT,
                'h2d_bytes_per_step': int(runner.h2d_bytes), 'd2h_bytes_per_step': int(runner.d2h_bytes),
                'ms_per_step': e_ms / args.steps}
+        del runner
+        # what bounds it: the host->device link.  Measured live with a plain pinned 256 MB copy (all ranks at once, like the run)
+        try:
+            hb = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+            db = torch.empty_like(hb, device=dev)
+            link = 0.0
+            for nbytes in (32 << 20, 64 << 20, 256 << 20):          # the runner moves 44-72 MB blocks; keep the best size
+                for _ in range(2):
+                    db[:nbytes].copy_(hb[:nbytes], non_blocking=True)
+                sync_all()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(8):
+                    db[:nbytes].copy_(hb[:nbytes], non_blocking=True)
+                c1.record()
+                sync_all()
+                link = max(link, 8 * nbytes / (c0.elapsed_time(c1) / 1e3) / 1e9)
+            e2e['h2d_link_gbps_measured'] = round(link, 1)
+            e2e['h2d_gbps_achieved'] = round(runner_gbps(e2e), 1)
+            e2e['h2d_link_frac'] = round(runner_gbps(e2e) / link, 3)
+            del hb, db
+        except Exception as e:      # noqa: BLE001
+            e2e['h2d_link_error'] = str(e)[:200]
 
     # ---- per-kernel breakdown and the roofline of the dominant kernel
     peak, peak_src = peaks()
@@ -506,6 +529,11 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def runner_gbps(e2e):
+    """host->device bytes per second per GPU of the e2e run."""
+    return e2e['h2d_bytes_per_step'] / (e2e['ms_per_step'] / 1e3) / 1e9
 
 
 def tensor_peak():
