@@ -123,13 +123,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference leg
-def cpu_reference_sample(wl, host, threads, sync=None):
+def cpu_reference_sample(wl, host, threads, sync=None, ref_kernels=False):
     """One full-size call of each kind through the oracle (reference algorithm in plain torch ops, fp32); returns
     (pairs_per_s extrapolated with the per-pair call counts, seconds spent, detail dict).  `host` on the CPU = the CPU
     baseline (all host threads); the same tensors on the GPU (sync = torch.cuda.synchronize) = the "PyTorch on the same
     GPU" baseline, which is what the reference's own pure-PyTorch QTAttB (quadtree_attention_smart.py) amounts to."""
     from oracle import cascade as ocas, fine as ofine, qtatt as oqt       # the checker, used here as the baseline
     torch.set_num_threads(threads)
+    qt_fn = lambda c: oqt.qtatt_b(c['q'], c['k'], c['v'], c['weight'], wl.topks, wl.nh8)
+    cas_fn = lambda c: oqt.cascade_qtatt_b(c['q'], c['k'], c['v'], c['topk_pos'], None, wl.nh4)
+    saved_score3d = ocas.ops.score3d
+    if ref_kernels:     # the reference's own data flow around its own CUDA extension kernels (oracle/_ref, built unmodified)
+        from oracle import ref_path
+        qt_fn = lambda c: ref_path.qtatt_b(c['q'], c['k'], c['v'], c['weight'], wl.topks, wl.nh8)
+        cas_fn = lambda c: ref_path.cascade_qtatt_b(c['q'], c['k'], c['v'], c['topk_pos'], wl.nh4)
+        ocas.ops.score3d = ref_path.score3d
     t = {}
     _pc = time.perf_counter
 
@@ -142,11 +150,11 @@ def cpu_reference_sample(wl, host, threads, sync=None):
     with torch.no_grad():
         c = host['qt'][0]
         t0 = time_now()
-        oqt.qtatt_b(c['q'], c['k'], c['v'], c['weight'], wl.topks, wl.nh8)
+        qt_fn(c)
         t['qtatt_b'] = time_now() - t0
         c = host['cas'][0]
         t0 = time_now()
-        _, idx01 = oqt.cascade_qtatt_b(c['q'], c['k'], c['v'], c['topk_pos'], None, wl.nh4)
+        _, idx01 = cas_fn(c)
         t['cascade_qtatt_b'] = time_now() - t0
         c1 = host['cas'][1]
         idx10 = oqt.quad_to_raster(oqt.cascade_window_idx(c1['topk_pos'], wl.h4, wl.w4).reshape(wl.B, 1, -1, 1, 100)
@@ -162,6 +170,7 @@ def cpu_reference_sample(wl, host, threads, sync=None):
         t0 = time_now()
         ofine.fine_match(host['fine']['feat_f0'][:M], host['fine']['feat_f1'][:M], r['mkpts1_c'][:M].float(), wl.H / wl.hf)
         t['fine_matching'] = time_now() - t0
+    ocas.ops.score3d = saved_score3d
     per_batch = wl.qt_calls * t['qtatt_b'] + wl.cas_calls * t['cascade_qtatt_b'] + t['cascade_matching'] + t['fine_matching']
     return wl.B / per_batch, sum(t.values()), {k: round(v, 4) for k, v in t.items()} | {'matches': int(M)}
 
@@ -515,10 +524,30 @@ def run_ours(args):
                                                   'QTAttB) on the same GPU, one call of each kind scaled by the call counts'}
         except Exception as e:      # noqa: BLE001  (out of memory etc.: the figure is optional)
             line['gpu_torch_baseline'] = {'error': str(e)[:200]}
+        try:        # the reference build on the same B200 = its data flow around its own extension kernels
+            from oracle import ref_path
+            if ref_path.available():
+                cpu_reference_sample(wl, dev_in, os.cpu_count() or 1, sync=torch.cuda.synchronize, ref_kernels=True)
+                v, spent, detail = cpu_reference_sample(wl, dev_in, os.cpu_count() or 1, sync=torch.cuda.synchronize, ref_kernels=True)
+                line['gpu_reference_kernels_baseline'] = {
+                    'value': v, 'unit': UNIT, 'seconds_per_call': detail,
+                    'speedup_eager_vs_eager': round(line['value_eager_instrumented'] / v, 1),
+                    'what': "the reference's GPU path on this B200: its QTAttB / CascadeQTAttB / ScoreComputation data flow (oracle/ref_path.py) "
+                            'calling its own three CUDA extensions built unmodified for sm_100a (oracle/_ref), eager, one call of each kind '
+                            'scaled by the call counts; matching post-processing and fine matching as plain torch CUDA ops'}
+            else:
+                line['gpu_reference_kernels_baseline'] = {'unavailable': 'oracle/_ref not built'}
+        except Exception as e:      # noqa: BLE001
+            line['gpu_reference_kernels_baseline'] = {'error': str(e)[:200]}
         torch.cuda.empty_cache()
-        v, spent, detail = cpu_reference_sample(wl, host, os.cpu_count() or 1)
+        runs, t_cpu = [], time.perf_counter()                 # bounded sample: ~10 s of host work, median of the repeats
+        while len(runs) < 2 or (time.perf_counter() - t_cpu < 10.0 and len(runs) < 16):
+            runs.append(cpu_reference_sample(wl, host, os.cpu_count() or 1))
+        runs = runs[1:]                                       # the first repeat warms the allocator and the thread pool
+        v = statistics.median(r[0] for r in runs)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
-                                'sample': SAMPLE_DESC, 'seconds_per_call': detail, 'seconds_spent': round(spent, 2)}
+                                'sample': SAMPLE_DESC + f'; median of {len(runs)} repeats', 'seconds_per_call': runs[-1][2],
+                                'seconds_spent': round(time.perf_counter() - t_cpu, 2)}
     else:
         line['cpu_baseline'] = None
     sys.stdout.flush()

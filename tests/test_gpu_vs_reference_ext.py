@@ -93,3 +93,20 @@ def test_cascade_stage_vs_reference_kernels(dev, ref):
     clear = (gap[..., 0] - gap[..., 1]) > 1e-6                                              # rows without an fp32 near-tie
     want_idx = torch.gather(up, 2, conf.argmax(dim=2, keepdim=True)).squeeze(-1)
     assert torch.equal(o['next_idx01'][clear], want_idx[clear])
+
+
+def test_reference_data_flow_restated(dev, ref):
+    """oracle/ref_path.py (the reference's QTAttB / CascadeQTAttB flow around its own kernels, used as the GPU baseline in
+    bench.py) computes what the oracle and the fused CUDA path compute."""
+    from oracle import qtatt as oqt, ref_path
+    B, nh, h, w, topks = 1, 4, 32, 48, [8, 8, 4]
+    qs, ks, vs, wt = synth.qtatt_inputs(B, nh * 32, h, w, 3, seed=61)
+    want = oqt.qtatt_b(qs, ks, vs, wt, topks, nh)
+    got = ref_path.qtatt_b([x.to(dev) for x in qs], [x.to(dev) for x in ks], [x.to(dev) for x in vs], wt.to(dev), topks, nh)
+    ours = F.qtatt_forward([x.to(dev) for x in qs], [x.to(dev) for x in ks], [x.to(dev) for x in vs], topks, nh, weight=wt.to(dev))
+    assert (got.cpu() - want).abs().max() < 1e-4 and (got - ours).abs().max() < 1e-4
+    d = synth.cascade_inputs(1, nh * 32, 32, 32, seed=62)
+    v = torch.randn(1, nh * 32, 32, 32, generator=torch.Generator().manual_seed(4))
+    wm, wu = oqt.cascade_qtatt_b(d['feat0'], d['feat1'], v, d['topk_pos01'], None, nh)
+    gm, gu = ref_path.cascade_qtatt_b(d['feat0'].to(dev), d['feat1'].to(dev), v.to(dev), d['topk_pos01'].to(dev), nh)
+    assert torch.equal(gu.cpu(), wu) and (gm.cpu() - wm).abs().max() < 1e-4
