@@ -423,6 +423,13 @@ def run_ours(args):
     qtatt_call = {'alg_bytes': wl.bytes_qtatt_call(), 'ms': round(qt_call_ms, 5),
                   'gbps': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6, 1),
                   'frac_of_hbm_peak': round(wl.bytes_qtatt_call() / qt_call_ms / 1e6 / peak, 4)}
+    # the other bound SURVEY 8d asks for: fp32 FMA throughput of the SIMT pipes (top-k selection rules out reduced precision)
+    S, L1, L0 = wl.h8 * wl.w8 // 16, wl.h8 * wl.w8 // 4, wl.h8 * wl.w8
+    qt_flops = wl.B * (4.0 * S * S * wl.C8 + 4.0 * wl.C8 * (L1 * 4 * wl.topks[0] + L0 * 4 * wl.topks[1]))
+    props = torch.cuda.get_device_properties(dev)
+    simt_peak = props.multi_processor_count * 128 * 2 * (clocks.get('sm_mhz') or 1965.0) * 1e6 / 1e12      # TFLOP/s at the clock under load
+    qtatt_call.update({'alg_flops': qt_flops, 'tflops': round(qt_flops / qt_call_ms / 1e9, 2), 'fp32_simt_peak_tflops': round(simt_peak, 1),
+                       'frac_of_fp32_simt_peak': round(qt_flops / qt_call_ms / 1e9 / simt_peak, 4)})
 
     # ---- SURVEY section 8f "next" #1, reported beside the hot path (not part of `value`): dense coarse matching statistics
     # of one pair at the 1/8 grid on the tensor cores
