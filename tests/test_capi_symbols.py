@@ -48,6 +48,35 @@ def test_argument_validation_needs_no_gpu():
     assert rc == -1                                                                  # null pointers
 
 
+def test_argument_validation_of_the_widening_entries():
+    """Same convention for the SURVEY 8f entry points: status code + message, before any CUDA call."""
+    from casmtr_b200 import _lib
+    lib = _lib.lib()
+    assert lib.casmtr_window_idx_fwd(None, None, 1, 16, 4, 4, 5, None) == -1                 # 5-window does not fit a 4x4 grid
+    assert b'window' in lib.casmtr_last_error_string()
+    assert lib.casmtr_window_idx_fwd(None, None, 1, 16, 8, 8, 4, None) == -1                 # even window
+    rc = lib.casmtr_cascade_qtatt_window_fwd(None, None, None, None, 7, None, None, None, 1, 4, 32, 16, 16, 16, 16, 0, None, 0, None)
+    assert rc == -2 and b'window 7' in lib.casmtr_last_error_string()                        # 49 candidates > 32
+    rc = lib.casmtr_cascade_qtatt_window_fwd(None, None, None, None, 5, None, None, None, 1, 4, 32, 16, 16, 8, 8, 0, None, 0, None)
+    assert rc == -1                                                                          # parent grid 4x4 cannot hold a 5-window
+    assert lib.casmtr_fine_window_gather(None, None, None, None, 4, 64, 32, 32, 16, 2, 4, None) == -1     # even W
+    assert lib.casmtr_fine_match_dev_fwd(None, None, None, None, None, 1.0, None, None, None, 8, 25, 64, None) == -1    # no count
+    assert lib.casmtr_pack_matches_dev(None, None, None, None, None, None, None, 0, 8, None, None) == -1
+    assert lib.casmtr_coarse_match_workspace_bytes(1, 0, 16, 256) == 0
+    d = _lib.QtattDesc()
+    d.B, d.nhead, d.D, d.levels, d.type = 1, 2, 32, 2, 0
+    d.qh[0] = d.qw[0] = d.kh[0] = d.kw[0] = 16
+    d.qh[1] = d.qw[1] = d.kh[1] = 8
+    d.kw[1] = 6                                                                              # not the 2x2 pooling of level 0
+    d.topks[0] = d.topks[1] = 4
+    one = ctypes.c_float(0)
+    p = ctypes.cast(ctypes.pointer(one), ctypes.c_void_p)
+    rc = lib.casmtr_qtatt_tokens_fwd(ctypes.byref(d), p, p, p, p, p, None, None, p, 1 << 30, None)
+    assert rc == -1 and b'2x level' in lib.casmtr_last_error_string()        # check_qtatt_desc already refuses it
+    prev = lib.casmtr_set_pdl(0)
+    assert lib.casmtr_set_pdl(prev) == 0 and lib.casmtr_set_pdl(prev) == prev
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from casmtr_b200 import _lib
     monkeypatch.setattr(_lib, '_lib', None)
