@@ -491,6 +491,22 @@ def run_ours(args):
                 'ms_per_call_topk_pos': t_pos, 'ms_per_call_next_idx': t_idx,
                 'what': 'CascadeQTAttB at 1/4 fed with the expanded window positions [B,L/4,25,2] (reference API) vs with next_idx [B,L/4] '
                         '(window expansion of get_window_warp_idx fused into the kernels, casmtr_cascade_qtatt_window_fwd)'}
+            # "next" #3, second half: the indoor config's relative position bias, as a tensor (get_relative_pe drop-in) vs computed
+            # inside the attention kernels from the two embedding tables
+            g = torch.Generator().manual_seed(8)
+            h8, w8 = wl.h4 // 2, wl.w4 // 2
+            pe = F.RelativePE(torch.randn(22, wl.nh4, generator=g).to(dev), torch.randn(22, wl.nh4, generator=g).to(dev), 10, nidx, (h8, w8), w8)
+            t_rp = _time(lambda: F.relative_pe(pe, cc['topk_pos'], (wl.h4, wl.w4)))
+            rp = F.relative_pe(pe, cc['topk_pos'], (wl.h4, wl.w4))
+            t_ten = _time(lambda: F.cascade_qtatt_forward(cc['q'], cc['k'], cc['v'], nidx, rp, wl.nh4))
+            t_fus = _time(lambda: F.cascade_qtatt_forward(cc['q'], cc['k'], cc['v'], nidx, pe, wl.nh4))
+            next_rows['relative_pe'] = {
+                'ms_bias_tensor_kernel': t_rp, 'ms_per_call_bias_tensor_input': t_ten, 'ms_per_call_bias_fused': t_fus,
+                'bias_tensor_bytes': rp.numel() * 4,
+                'what': 'CascadeQTAttB at 1/4 with the relative position bias of the indoor config: get_relative_pe materialised by one kernel '
+                        '(casmtr_relative_pe_fwd; ~25 torch ops in the reference) and read by the attention kernels, vs computed inside them '
+                        'from the two embedding tables (casmtr_cascade_qtatt_relpe_fwd)'}
+            del rp
             M = max(n_matches, 1)
             g = torch.Generator().manual_seed(9)
             ff = torch.randn(wl.B, 64, wl.hf, wl.wf, generator=g).to(dev)

@@ -32,6 +32,11 @@ class ExtractDesc(C.Structure):
                 ('scale', C.c_float), ('scale0', C.c_void_p), ('scale1', C.c_void_p)]
 
 
+class RelpeDesc(C.Structure):
+    _fields_ = [('w_table', C.c_void_p), ('h_table', C.c_void_p), ('tgt_idx', C.c_void_p), ('n_emb', C.c_int), ('LB', C.c_int),
+                ('h8', C.c_int), ('w8', C.c_int), ('w8_other', C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/casmtr_b200.h declares
 SIGNATURES = {
     'casmtr_version': (C.c_int, []),
@@ -58,6 +63,9 @@ SIGNATURES = {
     'casmtr_window_idx_fwd': (C.c_int, [c_i64_p, c_i64_p] + [C.c_int] * 5 + [C.c_void_p]),
     'casmtr_cascade_qtatt_window_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, C.c_int, c_float_p, c_float_p, c_i64_p]
                                         + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_relative_pe_fwd': (C.c_int, [C.POINTER(RelpeDesc), c_i64_p, c_float_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'casmtr_cascade_qtatt_relpe_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_i64_p, C.c_int, C.POINTER(RelpeDesc), c_float_p, c_i64_p]
+                                       + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_cascade_qtatt_workspace_bytes': (C.c_size_t, [C.c_int] * 6),
     'casmtr_cascade_qtatt_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                  + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),

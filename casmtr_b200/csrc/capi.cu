@@ -320,7 +320,8 @@ size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1
 static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
                               const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
                               int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
-                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx = nullptr, int win = 0);
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx = nullptr, int win = 0,
+                              const RelPE *pe = nullptr);
 
 int casmtr_window_idx_fwd(const int64_t *next_idx, int64_t *pos, int B, int L, int H, int W, int window, casmtr_stream_t stream) {
     CASMTR_REQUIRE(B >= 0 && L >= 0 && window >= 1 && (window & 1) && H >= window && W >= window, CASMTR_E_INVALID,
@@ -340,6 +341,50 @@ int casmtr_cascade_qtatt_window_fwd(const float *query, const float *key, const 
     CASMTR_REQUIRE(next_idx != nullptr, CASMTR_E_INVALID, "cascade_qtatt_window: null next_idx");
     return cascade_qtatt_impl(token_major != 0, query, key, value, nullptr, rel_pos, message, upsampled_idx, B, nhead, D, h0, w0, h1, w1,
                               window * window, 1, workspace, workspace_bytes, (cudaStream_t)stream, next_idx, window);
+}
+
+// casmtr_relpe_desc -> RelPE for an (h0 x w0) query level whose keys live on rows of w1 tokens
+static int relpe_from_desc(const casmtr_relpe_desc *d, int B, int nhead, int h0, int w0, int w1, RelPE *pe) {
+    CASMTR_REQUIRE(d != nullptr && d->w_table && d->h_table && d->tgt_idx, CASMTR_E_INVALID, "relative_pe: null descriptor / table / tgt_idx");
+    CASMTR_REQUIRE(B >= 1 && nhead >= 1 && d->h8 >= 1 && d->w8 >= 1 && d->w8_other >= 1 && d->n_emb >= 1 && d->LB >= 0, CASMTR_E_INVALID, "relative_pe: bad sizes");
+    CASMTR_REQUIRE(h0 % d->h8 == 0 && w0 == d->w8 * (h0 / d->h8), CASMTR_E_INVALID,
+                   "relative_pe: the %dx%d query level is not a multiple of the %dx%d 1/8 grid", h0, w0, d->h8, d->w8);
+    CASMTR_REQUIRE((h0 / d->h8) % 2 == 0, CASMTR_E_UNSUPPORTED, "relative_pe: level / 1/8-grid ratio %d must be even (2 at 1/4, 4 at 1/2)", h0 / d->h8);
+    CASMTR_REQUIRE(w1 == 0 || w1 == d->w8_other * (h0 / d->h8), CASMTR_E_INVALID,
+                   "relative_pe: key rows of %d tokens do not match w8_other * s = %d", w1, d->w8_other * (h0 / d->h8));
+    pe->w_tab = d->w_table; pe->h_tab = d->h_table; pe->tgt_idx = d->tgt_idx;
+    pe->n_emb = d->n_emb; pe->LB = d->LB; pe->s = h0 / d->h8; pe->h8 = d->h8; pe->w8 = d->w8; pe->w8o = d->w8_other;
+    return CASMTR_OK;
+}
+
+int casmtr_relative_pe_fwd(const casmtr_relpe_desc *d, const int64_t *window_pos, float *rel_pos,
+                           int B, int nhead, int h0, int w0, int k, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(h0 > 0 && w0 > 0 && h0 % 2 == 0 && w0 % 2 == 0 && k >= 1, CASMTR_E_INVALID, "relative_pe: the %dx%d level must be even, k >= 1", h0, w0);
+    CASMTR_REQUIRE(window_pos && rel_pos, CASMTR_E_INVALID, "relative_pe: null pointer");
+    RelPE pe;
+    const int rc = relpe_from_desc(d, B, nhead, h0, w0, 0, &pe);
+    if (rc != CASMTR_OK) return rc;
+    return launch_relative_pe(pe, window_pos, rel_pos, B, nhead, h0, w0, k, (cudaStream_t)stream);
+}
+
+int casmtr_cascade_qtatt_relpe_fwd(const float *query, const float *key, const float *value,
+                                   const int64_t *topk_pos, const int64_t *next_idx, int window, const casmtr_relpe_desc *d,
+                                   float *message, int64_t *upsampled_idx,
+                                   int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int token_major,
+                                   void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    CASMTR_REQUIRE((topk_pos != nullptr) != (next_idx != nullptr), CASMTR_E_INVALID, "cascade_qtatt_relpe: give topk_pos or next_idx, not both");
+    if (next_idx) {
+        CASMTR_REQUIRE(window >= 1 && (window & 1) && window * window <= 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt_relpe: window %d must be 1, 3 or 5", window);
+        CASMTR_REQUIRE(h1 % 2 == 0 && w1 % 2 == 0 && h1 / 2 >= window && w1 / 2 >= window, CASMTR_E_INVALID,
+                       "cascade_qtatt_relpe: the %dx%d key grid must be even and its parent grid must hold a %d-window", h1, w1, window);
+        k = window * window;
+    }
+    CASMTR_REQUIRE(h0 > 0 && w0 > 0 && w1 > 0, CASMTR_E_INVALID, "cascade_qtatt_relpe: bad sizes");
+    RelPE pe;
+    const int rc = relpe_from_desc(d, B, nhead, h0, w0, w1, &pe);
+    if (rc != CASMTR_OK) return rc;
+    return cascade_qtatt_impl(token_major != 0, query, key, value, topk_pos, nullptr, message, upsampled_idx, B, nhead, D, h0, w0, h1, w1,
+                              k, 1, workspace, workspace_bytes, (cudaStream_t)stream, next_idx, next_idx ? window : 0, &pe);
 }
 
 int casmtr_cascade_qtatt_fwd(const float *query, const float *key, const float *value,
@@ -363,7 +408,7 @@ int casmtr_cascade_qtatt_tokens_fwd(const float *query, const float *key, const 
 static int cascade_qtatt_impl(bool token_major, const float *query, const float *key, const float *value,
                               const int64_t *topk_pos, const float *rel_pos, float *message, int64_t *upsampled_idx,
                               int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int dilated,
-                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx, int win) {
+                              void *workspace, size_t workspace_bytes, cudaStream_t stream, const int64_t *next_idx, int win, const RelPE *pe) {
     CASMTR_REQUIRE(D == 32, CASMTR_E_UNSUPPORTED, "cascade_qtatt: head dim %d unsupported (D == 32)", D);
     CASMTR_REQUIRE(B >= 1 && nhead >= 1 && h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0, CASMTR_E_INVALID, "cascade_qtatt: bad sizes");
     CASMTR_REQUIRE(h0 % 2 == 0 && w0 % 2 == 0, CASMTR_E_INVALID, "cascade_qtatt: query grid %dx%d must be even", h0, w0);
@@ -395,13 +440,14 @@ static int cascade_qtatt_impl(bool token_major, const float *query, const float 
     memset(&fp, 0, sizeof(fp));
     fp.q = qt; fp.k = kt; fp.v = vt;
     fp.topk_pos = topk_pos; fp.next_idx = next_idx; fp.win = win; fp.rel_pos = rel_pos;
+    if (pe) fp.pe = *pe;
     fp.out = message; fp.upsampled_idx = upsampled_idx;
     fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1;
     fp.kp = k; fp.dil = dilated;
     if (k == 25 && dilated == 1 && ((uintptr_t)topk_pos & 15) == 0) {
         // regular 5x5 windows: TMA-tiled kernel for the coherent cells, gather kernel for the listed outliers
         int *fb_count = fb + (size_t)B * (h0 / 2) * (w0 / 2);
-        rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, next_idx, rel_pos, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
+        rc = launch_cascade_att_tile(qt, kt, vt, topk_pos, next_idx, rel_pos, fp.pe, message, upsampled_idx, fb, fb_count, B, nhead, h0, w0, h1, w1, stream);
         if (rc != CASMTR_OK) return rc;
         fp.item_list = fb; fp.item_count = fb_count;
     }

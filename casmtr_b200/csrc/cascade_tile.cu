@@ -35,6 +35,7 @@ struct TileParams {
     const int64_t *topk_pos;    // [B, Np, 25, 2]
     const int64_t *next_idx;    // [B, Np] instead of topk_pos: the 5x5 window is derived from the parent's match
     const float *rel_pos;       // [B, nh, h0*w0, 100] or NULL
+    RelPE pe;                   // or the bias computed from its embedding tables (pe.w_tab != NULL)
     float *out;                 // [B, h0*w0, C]
     int64_t *upsampled_idx;     // [B, h0*w0, 100] or NULL
     int *fb_list, *fb_count;    // fallback cells (b * Np + parent)
@@ -55,6 +56,7 @@ constexpr int SM_A = SM_META + 2 * NCONS * (int)sizeof(CellMeta) + 64; // float[
 constexpr int SM_BAR = ((SM_A + 15) / 16) * 16 + NCONS * KC * 4 * 4;  // uint64 full[2], empty[2]
 constexpr int SM_TOTAL = SM_BAR + 4 * 8;
 
+template <bool PE>                                         // PE: relative position bias from its embedding tables (p.pe)
 __global__ void __launch_bounds__((NCONS + 1) * 32, 1)     // 17 warps: one SM sub-partition holds 5 of them, which caps the kernel at 96 registers
 cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, TileParams p) {
@@ -228,6 +230,19 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     }
                 }
             }
+            if (PE) {                                         // the same bias from its embedding tables (get_relative_pe, transformer.py:473-509)
+                const int2 qt = relpe_query_term(p.pe, b, 2 * py, 2 * px);     // s is even: sibling f adds (f & 1, f >> 1)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int c = 32 * r + lane;
+                    if (c < KC) {
+                        const int kk = c >> 2, cf = c & 3;
+                        const int ky = 2 * (m.r0 + kk / 5) + (cf >> 1), kx = 2 * (m.c0 + kk % 5) + (cf & 1);
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) sc[r][f] += relpe_bias(p.pe, p.nh, h, qt, ky + (f >> 1), kx + (f & 1));
+                    }
+                }
+            }
             // ---- softmax over the 100 candidates per sibling
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
@@ -317,7 +332,7 @@ size_t cascade_tile_smem_bytes() { return 1024 + SM_TOTAL; }
 // Tile path of CascadeQTAttB for k == 25, dilated == 1.  q/k/v are the token-major copies.  Cells that cannot use their
 // block's tile are appended to fb_list (count in *fb_count, zeroed here); the caller runs the gather kernel over that list.
 int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const int64_t *next_idx, const float *rel_pos,
-                            float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
+                            const RelPE &pe, float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
                             int B, int nh, int h0, int w0, int h1, int w1, cudaStream_t stream) {
     const int C = nh * D;
     CUtensorMap tmK, tmV, tmQ;
@@ -326,7 +341,7 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     if (rc == CASMTR_OK) rc = make_tile_map(&tmQ, q, B, h0, w0, C, 2 * TP, 2 * TP, false);
     if (rc != CASMTR_OK) return rc;
     TileParams p;
-    p.topk_pos = topk_pos; p.next_idx = next_idx; p.rel_pos = rel_pos; p.out = out; p.upsampled_idx = upsampled_idx;
+    p.topk_pos = topk_pos; p.next_idx = next_idx; p.rel_pos = rel_pos; p.pe = pe; p.out = out; p.upsampled_idx = upsampled_idx;
     p.fb_list = fb_list; p.fb_count = fb_count;
     p.B = B; p.nh = nh; p.h0 = h0; p.w0 = w0; p.h1 = h1; p.w1 = w1;
     const int hp = h0 / 2, wp = w0 / 2;
@@ -334,8 +349,11 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     const size_t smem = cascade_tile_smem_bytes();
     static int n_sm = 0;
     if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(cascade_att_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_att_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaError_t e = cudaSuccess;
+        for (auto kern : {cascade_att_tile_kernel<false>, cascade_att_tile_kernel<true>}) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         int dev = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -346,7 +364,8 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     CASMTR_REQUIRE(n_work < 0x7fffffffLL, CASMTR_E_UNSUPPORTED, "cascade tile grid too large");
     const unsigned grid = (unsigned)(n_work < n_sm ? n_work : n_sm);          // persistent: one CTA per SM
     LaunchScope ls(CASMTR_K_CASCADE_ATT, stream);
-    launch_k(cascade_att_tile_kernel, grid, (NCONS + 1) * 32, smem, stream, tmK, tmV, tmQ, p);
+    if (pe.w_tab) launch_k(cascade_att_tile_kernel<true>, grid, (NCONS + 1) * 32, smem, stream, tmK, tmV, tmQ, p);
+    else launch_k(cascade_att_tile_kernel<false>, grid, (NCONS + 1) * 32, smem, stream, tmK, tmV, tmQ, p);
     CASMTR_CHECK_LAUNCH("cascade_att_tile_kernel");
     return CASMTR_OK;
 }

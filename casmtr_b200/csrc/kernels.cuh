@@ -44,6 +44,30 @@ struct CoarseParams {
 size_t coarse_smem_bytes(int Sk);
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
 
+// ---- relative position bias of the cascade cross attention, computed where it is consumed
+// (CascadeFeatureTransformer.get_relative_pe, src/model/modules/transformer.py:473-509; casmtr_relpe_desc)
+struct RelPE {
+    const float *w_tab, *h_tab; // [n_emb, nh]; w_tab == NULL: no bias
+    const int64_t *tgt_idx;     // [B, h8*w8]
+    int n_emb, LB, s;           // s = h0 / h8
+    int h8, w8, w8o;
+};
+#ifdef __CUDACC__
+// query-side part of the two table indices of query token (Y, X): (LB + X % s - tgt_x, LB + Y % s - tgt_y)   (:474-485, :500-503)
+__device__ __forceinline__ int2 relpe_query_term(const RelPE &pe, int b, int Y, int X) {
+    const int t = (int)__ldg(pe.tgt_idx + (size_t)b * pe.h8 * pe.w8 + (Y / pe.s) * pe.w8 + X / pe.s);
+    const int off = pe.s / 2 - 1;
+    const int ty = t / pe.w8o;
+    return make_int2(pe.LB + X % pe.s - ((t - ty * pe.w8o) * pe.s + off), pe.LB + Y % pe.s - (ty * pe.s + off));
+}
+// bias of key token (ky, kx) for head h: w_pos_bias[rx] + h_pos_bias[ry]   (:504-507)
+__device__ __forceinline__ float relpe_bias(const RelPE &pe, int nh, int h, int2 qt, int ky, int kx) {
+    const int rx = min(max(qt.x + kx, 0), pe.n_emb - 1), ry = min(max(qt.y + ky, 0), pe.n_emb - 1);
+    return __ldg(pe.w_tab + rx * nh + h) + __ldg(pe.h_tab + ry * nh + h);
+}
+#endif
+int launch_relative_pe(const RelPE &pe, const int64_t *window_pos, float *rel_pos, int B, int nh, int h0, int w0, int k, cudaStream_t stream);   // relpe.cu
+
 // ---- qtatt_fine.cu
 struct FineParams {
     const float *q;             // token-major raster [B, h0*w0, C]
@@ -55,6 +79,7 @@ struct FineParams {
                                 // image; the win x win window around it, shifted inside the grid, is derived in the kernel
     int win;                    // window side (kp == win * win) when next_idx is used
     const float *rel_pos;       // [B, nh, h0*w0, 4kp] or NULL (cascade)
+    RelPE pe;                   // cascade: the same bias computed from its embedding tables (pe.w_tab != NULL; rel_pos NULL then)
     const float *acc_prev;      // [B, Np, C] merged message of the coarser levels, or NULL (cascade)
     float *out;                 // [B, h0*w0, C] raster: acc_prev[parent] + w * message
     int *topk_idx;              // [B, h0*w0, nh, k] or NULL (last level / cascade)
@@ -83,7 +108,7 @@ __host__ __device__ inline int window_origin(int centre, int win, int n) {
 }
 int launch_window_idx(const int64_t *next_idx, int64_t *pos, size_t rows, int H, int W, int win, cudaStream_t stream);
 int launch_cascade_att_tile(const float *q, const float *k, const float *v, const int64_t *topk_pos, const int64_t *next_idx, const float *rel_pos,
-                            float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
+                            const RelPE &pe, float *out, int64_t *upsampled_idx, int *fb_list, int *fb_count,
                             int B, int nh, int h0, int w0, int h1, int w1, cudaStream_t stream);
 
 // ---- ops.cu

@@ -71,7 +71,7 @@ __host__ __device__ inline int warp_slab_floats(int kp) {
 }
 
 // KP > 0: compile-time number of parent candidates (gather loops fully unrolled); KP == 0: runtime p.kp
-template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK, bool PE = false>
 __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b, int parent, int h, int lane) {
     const int g = lane >> 3, dq = lane & 7;
     const int wp = p.w0 >> 1;
@@ -183,6 +183,20 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
             if (CASCADE && p.rel_pos != nullptr && valid)
                 s += __ldg(p.rel_pos + (((size_t)b * p.nh + h) * L0 + QTOK(f)) * KC + c);
             sc[r][f] = valid ? s : -INFINITY;
+        }
+    }
+    if (CASCADE && PE) {                            // the same bias from its embedding tables (get_relative_pe, transformer.py:473-509)
+        const int2 qt = relpe_query_term(p.pe, b, 2 * py, 2 * px);     // s is even: sibling f adds (f & 1, f >> 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int c = 32 * r + lane, cf = c & 3;
+            // the reference derives (row, col) from the flat, un-clamped child index (:489-499)
+            const int tok = __shfl_sync(FULL_MASK, base, (c >> 2) & 31) + (cf >> 1) * p.dil * p.w1 + (cf & 1) * p.dil;
+            const int ky = tok / p.w1, kx = tok - ky * p.w1;
+            if (c < KC) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) sc[r][f] += relpe_bias(p.pe, p.nh, h, qt, ky + (f >> 1), kx + (f & 1));
+            }
         }
     }
 
@@ -628,7 +642,7 @@ int launch_cta_t(const FineParams &p, cudaStream_t stream) {
 }
 
 // grid.x covers the (parent, head) items of one batch element, grid.y = batch
-template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK, bool PE = false>
 __global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int warps_per_cta) {
     pdl_sync();
     extern __shared__ __align__(16) float smem[];
@@ -637,11 +651,11 @@ __global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int w
     const unsigned item = blockIdx.x * (unsigned)warps_per_cta + warp;
     if (item >= (unsigned)(Np * p.nh)) return;
     const int parent = item / (unsigned)p.nh, h = item - parent * p.nh;
-    quad_item<KP, R, CASCADE, TYPE_A, DO_TOPK>(p, smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp), blockIdx.y, parent, h, lane);
+    quad_item<KP, R, CASCADE, TYPE_A, DO_TOPK, PE>(p, smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp), blockIdx.y, parent, h, lane);
 }
 
 // persistent variant over a device-side list of cells (b * Np + parent), all heads of each: the cascade fallback
-template <int KP, int R>
+template <int KP, int R, bool PE = false>
 __global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, int warps_per_cta) {
     pdl_sync();
     extern __shared__ __align__(16) float smem[];
@@ -651,12 +665,12 @@ __global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, 
     float *slab = smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp);
     for (int i = blockIdx.x * warps_per_cta + warp; i < n; i += gridDim.x * warps_per_cta) {
         const int cell = p.item_list[i / p.nh], h = i % p.nh;
-        quad_item<KP, R, true, false, false>(p, slab, cell / Np, cell % Np, h, lane);
+        quad_item<KP, R, true, false, false, PE>(p, slab, cell / Np, cell % Np, h, lane);
         __syncwarp();
     }
 }
 
-template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK>
+template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK, bool PE = false>
 int launch_t(const FineParams &p, cudaStream_t stream) {
     const long long items = (long long)(p.h0 / 2) * (p.w0 / 2) * p.nh;       // per batch element
     if (items == 0 || p.B == 0) return CASMTR_OK;
@@ -667,7 +681,7 @@ int launch_t(const FineParams &p, cudaStream_t stream) {
     const size_t smem = per_warp * wpc;
     const long long blocks = (items + wpc - 1) / wpc;
     CASMTR_REQUIRE(blocks <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
-    auto kern = quad_attention_kernel<KP, R, CASCADE, TYPE_A, DO_TOPK>;
+    auto kern = quad_attention_kernel<KP, R, CASCADE, TYPE_A, DO_TOPK, PE>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -681,13 +695,13 @@ int launch_t(const FineParams &p, cudaStream_t stream) {
     return CASMTR_OK;
 }
 
-template <int KP, int R>
+template <int KP, int R, bool PE>
 int launch_list_t(const FineParams &p, cudaStream_t stream) {
     const size_t per_warp = sizeof(float) * warp_slab_floats(p.kp);
     int wpc = (int)((113 * 1024) / per_warp);
     wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
     const size_t smem = per_warp * wpc;
-    auto kern = quad_attention_list_kernel<KP, R>;
+    auto kern = quad_attention_list_kernel<KP, R, PE>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -703,7 +717,8 @@ int launch_list_t(const FineParams &p, cudaStream_t stream) {
 
 template <int KP, int R>
 int launch_by_flags(const FineParams &p, cudaStream_t stream) {
-    if (p.topk_pos || p.next_idx) return launch_t<KP, R, true, false, false>(p, stream);       // cascade (gather path): warp per item
+    if (p.topk_pos || p.next_idx)                    // cascade (gather path): warp per item
+        return p.pe.w_tab ? launch_t<KP, R, true, false, false, true>(p, stream) : launch_t<KP, R, true, false, false>(p, stream);
     // QTAtt fine levels.  Intermediate levels (top-k, few items, long per-item chain): CTA per item, 4 warps = 4 siblings.
     // Last level (4x the items, no top-k): warp per item -- the CTA variant re-reads the K slab once per sibling warp and
     // becomes shared-memory-pipe bound there (ncu: l1tex 85 %), measured 69 us vs 64 us at 832^2.
@@ -719,7 +734,7 @@ int launch_quad_attention(const FineParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE((p.h0 % 2) == 0 && (p.w0 % 2) == 0, CASMTR_E_INVALID, "query grid %dx%d must be even", p.h0, p.w0);
     if (p.item_list) {                               // cascade fallback cells of the tile kernel
         CASMTR_REQUIRE((p.topk_pos || p.next_idx) && p.kp == 25, CASMTR_E_INVALID, "item lists are a cascade (k = 25) feature");
-        return launch_list_t<25, 4>(p, stream);
+        return p.pe.w_tab ? launch_list_t<25, 4, true>(p, stream) : launch_list_t<25, 4, false>(p, stream);
     }
     if (p.topk_idx) CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= 4 * p.kp, CASMTR_E_INVALID, "top-k %d must be in [1, min(32, %d)]", p.topk, 4 * p.kp);
     // the shipped configurations get fully unrolled gather loops; everything else runs the runtime-kp variant

@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ExtractDesc, QtattDesc, check, lib
+from ._lib import ExtractDesc, QtattDesc, RelpeDesc, check, lib
 
 
 def _stream(t):
@@ -222,11 +222,53 @@ def window_warp_idx(next_idx, H, W, window=5):
     return pos
 
 
+class RelativePE:
+    """What CascadeFeatureTransformer.get_relative_pe (reference transformer.py:473-509) reads besides the window: the two
+    embedding tables (w_pos_bias.weight / h_pos_bias.weight, [2*LB + sr_ratio, nhead]), LB, the query image's 1/8 match
+    tgt_idx [B,h8*w8] (data['stage_8c']['next_idx_c01' / 'next_idx_c10']) and the two 1/8 grids.  Pass it as `rel_pos` to
+    cascade_qtatt_forward and the bias is computed inside the attention kernels; relative_pe() materialises the tensor."""
+
+    def __init__(self, w_table, h_table, LB, tgt_idx, hw8, w8_other):
+        self.w_table = _chk(w_table.detach().to(torch.float32).contiguous(), 'w_table', torch.float32)
+        self.h_table = _chk(h_table.detach().to(torch.float32).contiguous(), 'h_table', torch.float32)
+        self.tgt_idx = _chk(tgt_idx, 'tgt_idx', torch.int64)
+        if self.w_table.dim() != 2 or self.w_table.shape != self.h_table.shape:
+            raise RuntimeError('w_table / h_table must both be [n_emb, nhead]')
+        self.LB, self.hw8, self.w8_other = int(LB), (int(hw8[0]), int(hw8[1])), int(w8_other)
+        if self.tgt_idx.dim() != 2 or self.tgt_idx.shape[1] != self.hw8[0] * self.hw8[1]:
+            raise RuntimeError(f'tgt_idx must be [B, h8*w8], got {tuple(self.tgt_idx.shape)}')
+
+    def desc(self, nhead, B):
+        if self.w_table.shape[1] != nhead or self.tgt_idx.shape[0] != B:
+            raise RuntimeError('relative PE tables / tgt_idx do not match nhead / batch')
+        d = RelpeDesc()
+        d.w_table, d.h_table, d.tgt_idx = self.w_table.data_ptr(), self.h_table.data_ptr(), self.tgt_idx.data_ptr()
+        d.n_emb, d.LB = self.w_table.shape[0], self.LB
+        d.h8, d.w8, d.w8_other = self.hw8[0], self.hw8[1], self.w8_other
+        return d
+
+
+def relative_pe(pe, window_pos, hw):
+    """get_relative_pe as a tensor: window_pos [B,(H/2)*(W/2),k,2] int64 (get_window_warp_idx output) -> [B,nhead,H*W,4k] fp32."""
+    _chk(window_pos, 'window_pos', torch.int64)
+    H, W = int(hw[0]), int(hw[1])
+    B, Np, k, two = window_pos.shape
+    if Np != (H // 2) * (W // 2) or two != 2:
+        raise RuntimeError(f'window_pos must be [B,(H/2)*(W/2),k,2], got {tuple(window_pos.shape)}')
+    nhead = pe.w_table.shape[1]
+    out = torch.empty(B, nhead, H * W, 4 * k, dtype=torch.float32, device=window_pos.device)
+    d = pe.desc(nhead, B)
+    with torch.cuda.device(window_pos.device):
+        check(lib().casmtr_relative_pe_fwd(C.byref(d), _ptr(window_pos), _ptr(out), B, nhead, H, W, k, _stream(out)), 'casmtr_relative_pe_fwd')
+    return out
+
+
 def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1, need_idx=True, hw_q=None, hw_k=None, window=5):
     """Fused CascadeQTAttB forward -> (message [B,h0*w0,C], upsampled_idx [B,h0*w0,4k] int64 or None).
     query / key / value: NCHW maps, or - with hw_q / hw_k given - token-major [B, h*w, C] (no transposes).
     topk_pos: [B,(h0/2)*(w0/2),k,2] window positions, or the 2-D next_idx [B,(h0/2)*(w0/2)] they are derived from
-    (the window x window expansion then happens inside the kernels; dilated must be 1)."""
+    (the window x window expansion then happens inside the kernels; dilated must be 1).
+    rel_pos: None, the reference's [B,nhead,h0*w0,4k] tensor, or a RelativePE (bias computed inside the kernels)."""
     _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(value, 'value', torch.float32)
     _chk(topk_pos, 'topk_pos', torch.int64)
     from_idx = topk_pos.dim() == 2
@@ -245,6 +287,11 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
             raise RuntimeError(f'next_idx must be [B,(h0/2)*(w0/2)] (got {tuple(topk_pos.shape)}) and dilated 1')
     elif topk_pos.shape != (B, (h0 // 2) * (w0 // 2), k, 2):
         raise RuntimeError(f'topk_pos must be [B,(h0/2)*(w0/2),k,2], got {tuple(topk_pos.shape)}')
+    fused_pe = rel_pos if isinstance(rel_pos, RelativePE) else None
+    if fused_pe is not None:
+        rel_pos = None
+        if (dilated or 1) != 1:
+            raise RuntimeError('the fused relative PE needs dilated == 1')
     if rel_pos is not None:
         rel_pos = _chk(rel_pos.to(torch.float32).contiguous(), 'rel_pos', torch.float32)
         if rel_pos.numel() != B * nhead * h0 * w0 * 4 * k:
@@ -255,6 +302,13 @@ def cascade_qtatt_forward(query, key, value, topk_pos, rel_pos, nhead, dilated=1
     with torch.cuda.device(dev):
         nbytes = lib().casmtr_cascade_qtatt_workspace_bytes(B, Cc, h0, w0, h1, w1)
         ws = _workspace(nbytes, dev)
+        if fused_pe is not None:
+            d = fused_pe.desc(nhead, B)
+            check(lib().casmtr_cascade_qtatt_relpe_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(None if from_idx else topk_pos),
+                                                       _ptr(topk_pos if from_idx else None), int(window), C.byref(d), _ptr(msg), _ptr(up),
+                                                       B, nhead, Cc // nhead, h0, w0, h1, w1, k, 1 if tokens else 0,
+                                                       _ptr(ws), ws.numel(), _stream(msg)), 'casmtr_cascade_qtatt_relpe_fwd')
+            return msg, up
         if from_idx:
             check(lib().casmtr_cascade_qtatt_window_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), int(window), _ptr(rel_pos), _ptr(msg), _ptr(up),
                                                         B, nhead, Cc // nhead, h0, w0, h1, w1, 1 if tokens else 0,

@@ -111,3 +111,34 @@ class CascadeQuadtreeAttention(nn.Module):
         msg, upsampled_idx = F.cascade_qtatt_forward(q, k, v, idx.contiguous(), rel_pos, self.num_heads,
                                                      dilated=self.cross_attn.dilated, hw_q=(H, W), hw_k=(H1, W1))
         return self.proj_drop(self.proj(msg)), upsampled_idx
+
+
+class CascadeRelativePE(nn.Module):
+    """The relative position bias of CascadeFeatureTransformer (reference src/model/modules/transformer.py: tables and LB
+    :356-362, get_window_warp_idx :416-440, get_relative_pe :473-509; indoor config only) -- SURVEY.md section 8f "next" #3.
+    Same parameter names (`h_pos_bias.weight`, `w_pos_bias.weight`), so the two tables load from a reference checkpoint
+    with the `coarse2.` / `coarse3.` prefix stripped.
+
+    get_relative_pe() is the drop-in (same arguments, returns the [B,nhead,HW,4ww] tensor, one kernel instead of ~25 torch
+    ops); fused() returns a handle to pass as `rel_pos` to CascadeQuadtreeAttention / CascadeQTAttB, in which case the bias
+    is computed inside the attention kernels and the tensor never exists."""
+
+    def __init__(self, nhead, window_size=5, sr_ratio=2):
+        super().__init__()
+        self.nhead, self.window_size, self.sr_ratio = nhead, window_size, sr_ratio
+        self.LB = window_size * 2 if sr_ratio == 2 else window_size * 6          # :357-360
+        self.h_pos_bias = nn.Embedding(self.LB * 2 + sr_ratio, nhead)
+        self.w_pos_bias = nn.Embedding(self.LB * 2 + sr_ratio, nhead)
+
+    def get_window_warp_idx(self, idx, B, H, W):
+        """idx [B,HW] -> ([B,HW,ww,2], None) (:416-440, 'window' propagation)."""
+        return F.window_warp_idx(idx.reshape(B, -1).contiguous(), H, W, self.window_size), None
+
+    def fused(self, data, i=0):
+        tgt = data['stage_8c']['next_idx_c01'] if i == 0 else data['stage_8c']['next_idx_c10']
+        return F.RelativePE(self.w_pos_bias.weight, self.h_pos_bias.weight, self.LB, tgt.contiguous(),
+                            data[f'hw{i}_8c'], data[f'hw{1 - i}_8c'][1])
+
+    def get_relative_pe(self, data, H, window_idx, device=None, i=0):
+        h, w = data[f'hw{i}_8c'][0], data[f'hw{i}_8c'][1]
+        return F.relative_pe(self.fused(data, i), window_idx.contiguous(), (H, w * (H // h)))

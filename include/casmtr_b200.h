@@ -197,6 +197,40 @@ CASMTR_API int casmtr_cascade_qtatt_window_fwd(const float *query, const float *
                              int B, int nhead, int D, int h0, int w0, int h1, int w1, int token_major,
                              void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* Relative position bias of the cascade cross attention (SURVEY 8f "next" #3; CascadeFeatureTransformer.get_relative_pe,
+ * src/model/modules/transformer.py:473-509; tables and LB from its constructor :356-362; indoor config only).  For query
+ * token (Y, X) of the current (h0 x w0) level and key token (ky, kx) of the other image's current level
+ *     t  = tgt_idx[b, (Y / s) * w8 + X / s],  s = h0 / h8           (the query's 1/8 match on the other image)
+ *     rx = X % s - ((t % w8_other) * s + s/2 - 1) + kx + LB,   ry likewise with Y, t / w8_other, ky
+ *     bias[b, head, token, candidate] = w_table[rx, head] + h_table[ry, head].
+ * The reference raises on a table index outside [0, n_emb); here it is clamped into the table. */
+typedef struct casmtr_relpe_desc {
+    const float *w_table;       /* w_pos_bias.weight [n_emb, nhead] */
+    const float *h_table;       /* h_pos_bias.weight [n_emb, nhead] */
+    const int64_t *tgt_idx;     /* [B, h8*w8] int64: data['stage_8c']['next_idx_c01' / 'next_idx_c10'] */
+    int n_emb;                  /* table rows = 2 * LB + sr_ratio */
+    int LB;
+    int h8, w8;                 /* 1/8 grid of the query image (h0 % h8 == 0, w0 == w8 * (h0 / h8)) */
+    int w8_other;               /* row length of the other image's 1/8 grid (w1 == w8_other * (h0 / h8)) */
+} casmtr_relpe_desc;
+
+/* Stand-alone drop-in for get_relative_pe: window_pos [B,(h0/2)*(w0/2),k,2] int64 (row, col on the previous level of the
+ * other image, the first output of get_window_warp_idx) -> rel_pos [B,nhead,h0*w0,4k] fp32, candidate order as in
+ * CascadeQTAttB (window entry major, then the 2x2 children row-major). */
+CASMTR_API int casmtr_relative_pe_fwd(const casmtr_relpe_desc *pe, const int64_t *window_pos, float *rel_pos,
+                           int B, int nhead, int h0, int w0, int k, casmtr_stream_t stream);
+
+/* CascadeQTAttB with the bias computed inside the attention kernels from the two embedding tables: the
+ * [B,nhead,h0*w0,4k] tensor (30.7 MB per pair and direction at 640x480) and the ~25 torch ops that build it never exist.
+ * Give topk_pos [B,(h0/2)*(w0/2),k,2] (next_idx NULL) or next_idx [B,(h0/2)*(w0/2)] with window in {1,3,5}
+ * (topk_pos NULL, k = window^2).  token_major as in casmtr_cascade_qtatt_window_fwd; dilated is 1 (the reference's
+ * get_relative_pe ignores dilation, transformer.py:489-493).  Workspace as casmtr_cascade_qtatt_workspace_bytes. */
+CASMTR_API int casmtr_cascade_qtatt_relpe_fwd(const float *query, const float *key, const float *value,
+                             const int64_t *topk_pos, const int64_t *next_idx, int window, const casmtr_relpe_desc *pe,
+                             float *message, int64_t *upsampled_idx,
+                             int B, int nhead, int D, int h0, int w0, int h1, int w1, int k, int token_major,
+                             void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- fused cascade matching (R6) */
 
 /* feat0 [B,L0,C], feat1 [B,L1,C] (un-normalised; the 1/sqrt(C) of reference :88 is applied inside);

@@ -4,6 +4,7 @@
   fine_windows              src/model/functions/fine_matching.py:47-66     (CascadeFinePreprocess.forward)
   quadtree_attention_layer  src/model/modules/quadtree_attention.py:68-99  (QuadtreeAttention.forward, type A / B)
   cascade_attention_layer   src/model/modules/quadtree_attention.py:152-171 (CascadeQuadtreeAttention.forward)
+  relative_pe               src/model/modules/transformer.py:473-509       (CascadeFeatureTransformer.get_relative_pe)
 
 Pinned against outputs of the reference's own modules (tests/golden/widen_*.npz, tests/golden/make_golden.py)."""
 import torch
@@ -77,3 +78,25 @@ def cascade_attention_layer(x, target, H, W, idx, sd, nhead, rel_pos=None, H1=No
     v = tF.conv2d(_nchw(target, H1, W1), sd['v_proj.weight'], sd.get('v_proj.bias'))
     msg, up = qtatt.cascade_qtatt_b(q.float(), k.float(), v.float(), idx, rel_pos, nhead, dilated)
     return tF.linear(msg.reshape(B, -1, C), sd['proj.weight'], sd['proj.bias']), up
+
+
+def relative_pe(window_pos, tgt_idx, w_table, h_table, LB, hw8, w8_other, H):
+    """window_pos [B,(H/2)*(W/2),k,2] int64 (row, col on the previous level of the other image), tgt_idx [B,h8*w8] int64 (the
+    query image's 1/8 match), w_table / h_table [n_emb,nhead] -> [B,nhead,H*W,4k] fp32.
+    :474-478 s, W1 and the query's position inside its 1/8 cell (x = col % s, y = row % s); :480-485 the match, brought to the
+    current level (* s + s//2 - 1); :487-499 the window's 2x2 children as flat indices, back to (x, y); :500-508
+    index = src - (tgt - window + LB) + 2 LB into the two tables, x table + y table."""
+    h8, w8 = hw8
+    s = H // h8
+    W, W1 = w8 * s, w8_other * s
+    B, Np, k, _ = window_pos.shape
+    Y, X = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    Y, X = Y.reshape(-1), X.reshape(-1)                                              # [HW]
+    t = tgt_idx[:, (Y // s) * w8 + X // s]                                           # [B,HW]
+    tx, ty = (t % w8_other) * s + (s // 2 - 1), torch.div(t, w8_other, rounding_mode='trunc') * s + (s // 2 - 1)
+    wp = window_pos[:, (Y // 2) * (W // 2) + X // 2] * 2                             # [B,HW,k,2]
+    kids = torch.stack([(wp[..., 0] + x) * W1 + wp[..., 1] + y for x in (0, 1) for y in (0, 1)], dim=3).reshape(B, H * W, 4 * k)
+    kx, ky = kids % W1, torch.div(kids, W1, rounding_mode='trunc')
+    rx = (X % s)[None, :, None] - (tx[:, :, None] - kx + LB) + 2 * LB
+    ry = (Y % s)[None, :, None] - (ty[:, :, None] - ky + LB) + 2 * LB
+    return (w_table[rx] + h_table[ry]).permute(0, 3, 1, 2).contiguous()               # [B,nhead,HW,4k]

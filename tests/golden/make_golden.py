@@ -231,6 +231,67 @@ def gen_widen(ref):
          cas_x=xc, cas_target=tc, cas_topk_pos=d['topk_pos01'], cas_out=co, cas_upsampled_idx=cup, **out)
 
 
+def gen_relative_pe(ref):
+    """get_window_warp_idx + get_relative_pe of the reference's CascadeFeatureTransformer, unbound on a stand-in that carries
+    what they read (window, LB, the two nn.Embedding tables), followed by the reference's CascadeQTAttB with that bias.
+    Case s2: the 4c stage (window and target from the same 1/8 matches, LB = 10); case s4: the 2c stage (window from 1/4
+    matches, target from the 1/8 matches, LB = 30).  Images of different sizes so the two grids cannot be confused."""
+    tr = __import__('src.model.modules.transformer', fromlist=['CascadeFeatureTransformer'])
+    prop = __import__('src.model.modules.propagations', fromlist=['get_propagations'])
+    window, full = prop.get_propagations({'propagation': 'window', 'window_size': 5, 'dilated': 1})
+    g = torch.Generator().manual_seed(21)
+    B, nh = 2, 2
+    hw8 = [(6, 8), (7, 9)]
+    out = {}
+    for tag, s, sr in (('s2', 2, 2), ('s4', 4, 4)):
+        class Stand:
+            pass
+        st = Stand()
+        st.window, st.full_window = window, full
+        st.LB = 5 * 2 if sr == 2 else 5 * 6                              # transformer.py:357-360
+        st.w_pos_bias = torch.nn.Embedding(st.LB * 2 + sr, nh)
+        st.h_pos_bias = torch.nn.Embedding(st.LB * 2 + sr, nh)
+        with torch.no_grad():
+            st.w_pos_bias.weight.copy_(torch.randn(st.LB * 2 + sr, nh, generator=g))
+            st.h_pos_bias.weight.copy_(torch.randn(st.LB * 2 + sr, nh, generator=g))
+        out[f'{tag}_w_table'], out[f'{tag}_h_table'] = st.w_pos_bias.weight.detach(), st.h_pos_bias.weight.detach()
+        data = {'hw0_8c': hw8[0], 'hw1_8c': hw8[1], 'stage_8c': {}}
+        for i in (0, 1):
+            (h, w), (ho, wo) = hw8[i], hw8[1 - i]
+            # a coherent match field (scaled identity + shift) with 15 % random entries: tile and fallback cells both occur
+            yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+            ty = (yy * ho // h + 1).clamp(0, ho - 1)
+            tx = (xx * wo // w - 1).clamp(0, wo - 1)
+            t8 = (ty * wo + tx).reshape(1, -1).repeat(B, 1)
+            rnd = torch.rand(B, h * w, generator=g) < 0.15
+            t8 = torch.where(rnd, torch.randint(0, ho * wo, (B, h * w), generator=g), t8)
+            data['stage_8c']['next_idx_c01' if i == 0 else 'next_idx_c10'] = t8
+        for i in (0, 1):
+            (h, w), (ho, wo) = hw8[i], hw8[1 - i]
+            t8 = data['stage_8c']['next_idx_c01' if i == 0 else 'next_idx_c10']
+            H, W, H1, W1 = h * s, w * s, ho * s, wo * s                  # current level of the query / the other image
+            if s == 2:
+                prev_idx = t8                                            # the 4c stage windows around the 1/8 matches
+            else:                                                        # the 2c stage windows around 1/4 matches near the 1/8 ones
+                t8u = t8.reshape(B, h, 1, w, 1).expand(B, h, 2, w, 2).reshape(B, -1)
+                py = (torch.div(t8u, wo, rounding_mode='trunc') * 2 + torch.randint(-3, 5, t8u.shape, generator=g)).clamp(0, ho * 2 - 1)
+                px = (t8u % wo * 2 + torch.randint(-3, 5, t8u.shape, generator=g)).clamp(0, wo * 2 - 1)
+                prev_idx = py * (wo * 2) + px
+            pos, _ = tr.CascadeFeatureTransformer.get_window_warp_idx(st, prev_idx, B, H1 // 2, W1 // 2)
+            with torch.no_grad():
+                rp = tr.CascadeFeatureTransformer.get_relative_pe(st, data, H, pos, torch.device('cpu'), i=i)
+            if s == 4 and i == 1:                                         # keep the fixture small: one direction at the 2c stage
+                continue
+            q = torch.randn(B, nh * 32, H, W, generator=g)
+            k = torch.randn(B, nh * 32, H1, W1, generator=g)
+            v = torch.randn(B, nh * 32, H1, W1, generator=g)
+            with torch.no_grad():
+                msg, up = ref.CascadeQTAttB(nh, 32, dilated=1)(q, k, v, pos, rp.to(torch.float32))
+            out.update({f'{tag}_{i}_tgt_idx': t8, f'{tag}_{i}_prev_idx': prev_idx, f'{tag}_{i}_pos': pos, f'{tag}_{i}_rel_pos': rp,
+                        f'{tag}_{i}_q': q, f'{tag}_{i}_k': k, f'{tag}_{i}_v': v, f'{tag}_{i}_msg': msg})
+    save('widen_relative_pe', hw8=torch.tensor(hw8), nhead=torch.tensor(nh), **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -241,3 +302,4 @@ if __name__ == '__main__':
     gen_fine(ref)
     gen_windows(ref)
     gen_widen(ref)
+    gen_relative_pe(ref)

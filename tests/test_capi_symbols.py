@@ -77,6 +77,29 @@ def test_argument_validation_of_the_widening_entries():
     assert lib.casmtr_set_pdl(prev) == 0 and lib.casmtr_set_pdl(prev) == prev
 
 
+def test_argument_validation_of_the_relative_pe_entries():
+    from casmtr_b200 import _lib
+    lib = _lib.lib()
+    one = ctypes.c_float(0)
+    p = ctypes.cast(ctypes.pointer(one), ctypes.c_void_p)
+    d = _lib.RelpeDesc()
+    d.w_table, d.h_table, d.tgt_idx = p, p, p
+    d.n_emb, d.LB, d.h8, d.w8, d.w8_other = 22, 10, 6, 8, 9
+    assert lib.casmtr_relative_pe_fwd(None, p, p, 1, 2, 12, 16, 25, None) == -1                 # no descriptor
+    assert lib.casmtr_relative_pe_fwd(ctypes.byref(d), p, p, 1, 2, 12, 18, 25, None) == -1      # w0 != w8 * s
+    assert b'1/8 grid' in lib.casmtr_last_error_string()
+    assert lib.casmtr_relative_pe_fwd(ctypes.byref(d), p, p, 1, 2, 18, 24, 25, None) == -2      # s = 3
+    assert b'must be even' in lib.casmtr_last_error_string()
+    args = (1, 2, 32, 12, 16, 14, 20, 25, 0, None, 0, None)                                      # w1 = 20 != w8_other * s = 18
+    assert lib.casmtr_cascade_qtatt_relpe_fwd(p, p, p, p, None, 0, ctypes.byref(d), p, None, *args) == -1
+    assert b'w8_other' in lib.casmtr_last_error_string()
+    args = (1, 2, 32, 12, 16, 14, 18, 25, 0, None, 0, None)
+    assert lib.casmtr_cascade_qtatt_relpe_fwd(p, p, p, p, p, 5, ctypes.byref(d), p, None, *args) == -1      # topk_pos AND next_idx
+    assert lib.casmtr_cascade_qtatt_relpe_fwd(p, p, p, None, p, 7, ctypes.byref(d), p, None, *args) == -2   # window 7
+    assert lib.casmtr_cascade_qtatt_relpe_fwd(p, p, p, p, None, 0, ctypes.byref(d), p, None, *args) == -1   # passes the PE checks, no workspace
+    assert b'null pointer' in lib.casmtr_last_error_string()
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from casmtr_b200 import _lib
     monkeypatch.setattr(_lib, '_lib', None)
