@@ -47,6 +47,60 @@ int casmtr_set_pdl(int on) {
     return prev;
 }
 
+// ---- fork / join onto a library-owned side stream (casmtr_set_overlap).  A fused call whose first kernel needs only part of
+// the re-laid inputs forks the rest of the layout work onto a side stream and joins it back before the first consumer, so the
+// HBM-bound transposes run under the issue-bound first kernel.  Everything stays ordered with respect to the caller's stream:
+// the fork waits for the caller's stream, the caller's stream waits for the join.  Both are event record / wait pairs, legal
+// inside a stream capture (the side stream joins the capture and leaves it at the join).  Lanes are created once per device,
+// outside any capture where possible (casmtr_set_overlap(1) or the first eager call), and handed out round-robin.
+namespace {
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
+constexpr int SIDE_LANES = 8, SIDE_MAX_DEV = 16;
+std::mutex g_side_mu;
+SideLane g_side[SIDE_MAX_DEV][SIDE_LANES];
+bool g_side_ready[SIDE_MAX_DEV];
+unsigned g_side_next[SIDE_MAX_DEV];
+std::atomic<int> g_overlap{-1};
+
+bool overlap_enabled() {
+    int v = g_overlap.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("CASMTR_OVERLAP");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_overlap.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+
+// a lane of the current device, or nullptr (overlap off / lanes unavailable: the caller then stays on its own stream)
+SideLane *side_lane() {
+    if (!overlap_enabled()) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SIDE_MAX_DEV) return nullptr;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (!g_side_ready[dev]) {
+        for (int i = 0; i < SIDE_LANES; ++i) {
+            SideLane &l = g_side[dev][i];
+            if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        g_side_ready[dev] = true;
+    }
+    return &g_side[dev][g_side_next[dev]++ % SIDE_LANES];
+}
+}  // namespace
+
+int casmtr_set_overlap(int on) {
+    const int prev = overlap_enabled() ? 1 : 0;
+    g_overlap.store(on ? 1 : 0, std::memory_order_relaxed);
+    if (on) side_lane();                    // create the lanes now (outside a stream capture)
+    return prev;
+}
+
 void casmtr_prof_begin(int kind, cudaStream_t stream, int *slot) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     *slot = -1;
@@ -201,7 +255,7 @@ size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc) {
 
 // the levels themselves, on token-major pyramids bf.q/k/v
 static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream);
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join = nullptr);
 
 int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
                      const float *const *queries, const float *const *keys, const float *const *values,
@@ -219,17 +273,43 @@ int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "qtatt: workspace %zu < %zu bytes", workspace_bytes, ws.off);
     const int C = d->nhead * d->D;
 
-    TransposeJobs jobs;
-    jobs.n = 0;
-    for (int l = 0; l < d->levels; ++l) {
-        CASMTR_REQUIRE(queries[l] && keys[l] && values[l], CASMTR_E_INVALID, "qtatt: null level pointer %d", l);
+    for (int l = 0; l < d->levels; ++l) CASMTR_REQUIRE(queries[l] && keys[l] && values[l], CASMTR_E_INVALID, "qtatt: null level pointer %d", l);
+    auto add_level = [&](TransposeJobs &jobs, int l) {
         jobs.job[jobs.n++] = TransposeJob{queries[l], bf.q[l], C, d->qh[l] * d->qw[l], 0};
         jobs.job[jobs.n++] = TransposeJob{keys[l], bf.k[l], C, d->kh[l] * d->kw[l], 0};
         jobs.job[jobs.n++] = TransposeJob{values[l], bf.v[l], C, d->kh[l] * d->kw[l], 0};
+    };
+    TransposeJobs jobs;
+    jobs.n = 0;
+    // The dense coarsest level needs only the coarsest maps (1/16 of the finest): with a side lane the finer levels' maps
+    // (95 % of the bytes, HBM-bound) are re-laid under the coarsest level's kernel (issue-bound) and joined before the first
+    // fine level.  Without a lane: one batched launch on the caller's stream.
+    SideLane *lane = d->levels >= 2 ? side_lane() : nullptr;
+    if (lane && (cudaEventRecord(lane->fork, stream) != cudaSuccess || cudaStreamWaitEvent(lane->stream, lane->fork, 0) != cudaSuccess)) {
+        cudaGetLastError();
+        lane = nullptr;
+    }
+    if (lane) {
+        for (int l = 0; l + 1 < d->levels; ++l) add_level(jobs, l);
+        rc = launch_transpose_jobs(jobs, d->B, lane->stream);
+        // the join is recorded and waited for even after a failed launch: a capture must never be left with a dangling fork
+        const bool joined = cudaEventRecord(lane->join, lane->stream) == cudaSuccess;
+        if (rc != CASMTR_OK || !joined) {
+            if (joined) cudaStreamWaitEvent(stream, lane->join, 0);
+            if (rc == CASMTR_OK) { casmtr_set_error("qtatt: cudaEventRecord on the side stream failed"); rc = CASMTR_E_CUDA; }
+            return rc;
+        }
+        jobs.n = 0;
+        add_level(jobs, d->levels - 1);
+    } else {
+        for (int l = 0; l < d->levels; ++l) add_level(jobs, l);
     }
     rc = launch_transpose_jobs(jobs, d->B, stream);
-    if (rc != CASMTR_OK) return rc;
-    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
+    if (rc != CASMTR_OK) {
+        if (lane) cudaStreamWaitEvent(stream, lane->join, 0);
+        return rc;
+    }
+    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream, lane ? lane->join : nullptr);
 }
 
 int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const float *k0, const float *v0,
@@ -264,11 +344,25 @@ int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const f
     return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
 }
 
+static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
+                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join);
+
 static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream) {
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join) {
+    const int rc = qtatt_levels_impl(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream, join);
+    if (join) cudaStreamWaitEvent(stream, join, 0);     // an early error return must not leave the side lane un-joined
+    return rc;
+}
+
+static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
+                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join) {
     int rc = CASMTR_OK;
     const float *wts = d->type == 0 ? level_weight : nullptr;
     for (int i = 0; i < d->levels; ++i) {
+        if (join && i == 1) {                           // the finer levels' maps come from the side lane (casmtr_qtatt_fwd)
+            if (cudaStreamWaitEvent(stream, join, 0) != cudaSuccess) { casmtr_set_error("qtatt: cudaStreamWaitEvent(join) failed"); return CASMTR_E_CUDA; }
+            join = nullptr;
+        }
         const int l = d->levels - 1 - i;
         const bool last = i == d->levels - 1;
         float *dst = last ? out : bf.acc[i];

@@ -51,6 +51,12 @@ def set_pdl(on):
     return bool(lib().casmtr_set_pdl(1 if on else 0))
 
 
+def set_overlap(on):
+    """Side-stream overlap of the finer levels' transposes with the coarsest level inside casmtr_qtatt_fwd (casmtr_set_overlap);
+    returns the previous setting.  Call it once outside any CUDA-graph capture: it creates the library's side streams."""
+    return bool(lib().casmtr_set_overlap(1 if on else 0))
+
+
 def profile_collect():
     """-> {kind_name: (device_ms, launches)} accumulated since the last collect (synchronises)."""
     ms = (C.c_double * _lib.K_COUNT)()

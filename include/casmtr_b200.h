@@ -160,6 +160,14 @@ CASMTR_API int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *desc, const floa
  * stream could use).  Returns the previous setting. */
 CASMTR_API int casmtr_set_pdl(int on);
 
+/* Layout / compute overlap inside casmtr_qtatt_fwd: when on (default; CASMTR_OVERLAP=0 in the environment turns it off) the
+ * call forks the NCHW -> token-major transposes of all but the coarsest pyramid level onto a library-owned side stream and
+ * joins them back before the first fine level, so they run under the coarsest level's kernel.  The call stays fully ordered
+ * with respect to the caller's stream (event fork after the caller's prior work, event join before the call's later kernels
+ * and anything the caller enqueues afterwards) and can be stream-captured.  Turning it on creates the side streams (8 per
+ * device) if they do not exist yet -- do that outside a capture.  Returns the previous setting. */
+CASMTR_API int casmtr_set_overlap(int on);
+
 /* ---------------------------------------------------------------- fused cascade window attention (R5) */
 
 CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1);

@@ -73,3 +73,41 @@ def test_cascade_qtatt_b(dev, B, nh, h, w, rel, dil):
     out_m, out_i = m(d['feat0'].to(dev), d['feat1'].to(dev), v.to(dev), d['topk_pos01'].to(dev), None if rp is None else rp.to(dev))
     assert torch.equal(out_i.cpu(), ref_i)                      # integer work: bit-exact
     assert (out_m.cpu() - ref_m).abs().max() < TOL
+
+
+def test_side_stream_overlap_is_equivalent_and_capturable(dev):
+    """casmtr_set_overlap: the finer levels' transposes on the library's side stream must give bit-identical results, stay
+    ordered with the caller's stream (inputs produced just before the call, outputs consumed just after it) and be legal
+    inside a CUDA-graph capture of the caller's stream."""
+    topks, nh, h, w = [16, 8, 8], 4, 32, 48
+    qs, ks, vs, wt = synth.qtatt_inputs(2, nh * 32, h, w, 3, seed=17)
+    qs, ks, vs, wt = _cuda(qs, dev), _cuda(ks, dev), _cuda(vs, dev), wt.to(dev)
+    prev = F.set_overlap(False)
+    try:
+        want = F.qtatt_forward(qs, ks, vs, topks, nh, weight=wt)
+        F.set_overlap(True)
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(3):                                  # back-to-back calls rotate through the side lanes
+                q2 = [t * 1.0 for t in qs]                      # produced on the caller's stream right before the call
+                got = F.qtatt_forward(q2, ks, vs, topks, nh, weight=wt)
+                total = got.sum()                               # consumed right after it
+        s.synchronize()
+        assert torch.equal(got, want) and torch.isfinite(total)
+        g = torch.cuda.CUDAGraph()
+        static_q = [t.clone() for t in qs]
+        with torch.cuda.graph(g):
+            cap = F.qtatt_forward(static_q, ks, vs, topks, nh, weight=wt)
+        cap.zero_()
+        g.replay()
+        torch.cuda.synchronize(dev)
+        assert torch.equal(cap, want)
+        for t in static_q:
+            t.mul_(0.5)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        F.set_overlap(False)
+        assert torch.equal(cap, F.qtatt_forward(static_q, ks, vs, topks, nh, weight=wt))
+    finally:
+        F.set_overlap(prev)
