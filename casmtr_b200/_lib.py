@@ -77,6 +77,8 @@ SIGNATURES = {
     'casmtr_coarse_match_workspace_bytes': (C.c_size_t, [C.c_int] * 4),
     'casmtr_coarse_match_fwd': (C.c_int, [c_float_p, c_float_p, C.c_float, c_float_p, c_i64_p, c_float_p, c_i64_p]
                                 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_coarse_match_masked_fwd': (C.c_int, [c_float_p, c_float_p, c_u8_p, c_u8_p, C.c_float, c_float_p, c_i64_p, c_float_p, c_i64_p]
+                                       + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_match_extract_workspace_bytes': (C.c_size_t, [C.POINTER(ExtractDesc)]),
     'casmtr_match_extract': (C.c_int, [C.POINTER(ExtractDesc), c_float_p, c_i64_p, c_i64_p, c_u8_p, c_i64_p, c_i64_p, c_i64_p,
                                        c_float_p, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

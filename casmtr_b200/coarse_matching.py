@@ -5,7 +5,8 @@ tensor cores without materialising the matrix (casmtr_coarse_match_fwd).
 
 What is NOT produced: `conf_matrix` and the mutual-nearest-neighbour match list of get_coarse_match (:91-153).  In the cascade
 models they feed the training supervision only (the final matches come from the last cascade stage); they are set to None.
-Masks (padded images) are not supported by the fused kernel yet and raise."""
+Padding masks (mask_c0 / mask_c1, reference :64-65) are applied inside the kernel: padded columns take no part, padded rows
+come out as the reference's constant -1e9 rows do (uniform soft-max: next_conf 1 / columns, next_idx 0)."""
 import torch.nn as nn
 
 from . import functional as F
@@ -29,9 +30,9 @@ class CoarseMatching(nn.Module):
         next_conf_c01/c10 fp32 (reference :70-84)."""
         if self.training:
             raise NotImplementedError('casmtr_b200.CoarseMatching implements the inference statistics only')
-        if mask_c0 is not None or mask_c1 is not None:
-            raise NotImplementedError('casmtr_b200.CoarseMatching: padding masks are not supported by the fused kernel')
-        o = F.coarse_match_forward(feat_c0.float().contiguous(), feat_c1.float().contiguous(), self.temperature)
+        if (mask_c0 is None) != (mask_c1 is None):
+            raise RuntimeError('CoarseMatching: the reference masks with mask_c0 * mask_c1 (:65), give both or neither')
+        o = F.coarse_match_forward(feat_c0.float().contiguous(), feat_c1.float().contiguous(), self.temperature, mask_c0, mask_c1)
         data[f'stage_{level}'] = {
             'conf_matrix': None, 'next_conf_c01_topk': None, 'next_idx_c01_topk': None,
             'next_conf_c10_topk': None, 'next_idx_c10_topk': None,

@@ -593,12 +593,20 @@ size_t casmtr_coarse_match_workspace_bytes(int B, int L0, int L1, int C) {
 int casmtr_coarse_match_fwd(const float *feat0, const float *feat1, float temperature,
                             float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
                             int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    return casmtr_coarse_match_masked_fwd(feat0, feat1, nullptr, nullptr, temperature, next_conf01, next_idx01, next_conf10, next_idx10,
+                                          B, L0, L1, C, workspace, workspace_bytes, stream);
+}
+
+int casmtr_coarse_match_masked_fwd(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1, float temperature,
+                                   float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                                   int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
     CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0, CASMTR_E_INVALID, "coarse_match: bad sizes");
+    CASMTR_REQUIRE((mask0 == nullptr) == (mask1 == nullptr), CASMTR_E_INVALID, "coarse_match: give both masks or neither");
     CASMTR_REQUIRE(feat0 && feat1 && next_conf01 && next_idx01 && next_conf10 && next_idx10 && workspace, CASMTR_E_INVALID,
                    "coarse_match: null pointer");
     CASMTR_REQUIRE(temperature > 0.f, CASMTR_E_INVALID, "coarse_match: temperature must be positive");
     CASMTR_REQUIRE(2 * B <= 65535, CASMTR_E_UNSUPPORTED, "coarse_match: batch too large");
-    return launch_coarse_match(feat0, feat1, temperature, next_conf01, next_idx01, next_conf10, next_idx10, B, L0, L1, C,
+    return launch_coarse_match(feat0, feat1, mask0, mask1, temperature, next_conf01, next_idx01, next_conf10, next_idx10, B, L0, L1, C,
                                workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

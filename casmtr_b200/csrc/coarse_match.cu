@@ -35,6 +35,8 @@ struct CoarseStatParams {
     int *parg;
     int B, L[2], C, nsplit, Lmax;
     float scale_log2;           // log2(e) / (C * temperature)
+    const uint32_t *mbits[2];   // padding masks of image 0 / 1 packed 32 tokens per word ([B][mwords]), or NULL (reference :64-65)
+    int mwords[2];
 };
 
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_co
         const int row = row0 + 32 * q + lane;
         float m = -INFINITY, l = 0.f;
         int arg = 0;
+        const uint32_t *cmask = p.mbits[1 - dir] ? p.mbits[1 - dir] + (size_t)b * p.mwords[1 - dir] : nullptr;
         for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
             const int a = it & 1;
             mbar_wait(tfull + a, (it >> 1) & 1);
@@ -171,11 +174,13 @@ __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_co
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + a * BN + 32 * c, v);
                 const int col0 = t * BN + 32 * c;
+                // masked columns take no part (masked_fill_(-1e9) underflows to 0 in the soft-max, reference :64-65); col0 is a multiple of 32 = one mask word
+                const uint32_t cbits = (cmask != nullptr && col0 < Lc) ? __ldg(cmask + (col0 >> 5)) : 0xffffffffu;
                 float cm = -INFINITY;
                 int ca = 0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    v[i] = col0 + i < Lc ? v[i] * p.scale_log2 : -INFINITY;
+                    v[i] = (col0 + i < Lc && ((cbits >> i) & 1u)) ? v[i] * p.scale_log2 : -INFINITY;
                     if (v[i] > cm) { cm = v[i]; ca = i; }
                 }
                 if (cm > m) { l *= exp2f(m - cm); m = cm; arg = col0 + ca; }
@@ -232,8 +237,22 @@ __global__ void coarse_merge_kernel(CoarseStatParams p, float *conf01, int64_t *
         const size_t o = ((size_t)(dir * p.nsplit + s) * p.B + b) * p.Lmax + row;
         if (p.pmax[o] > -INFINITY) l += p.psum[o] * exp2f(p.pmax[o] - m);
     }
-    (dir ? conf10 : conf01)[i] = 1.0f / l;
-    (dir ? idx10 : idx01)[i] = arg;
+    // the reference fills with -INF = -1e9 (coarse_matching.py:6), not -infinity: a padded row (or a row whose columns are all
+    // padded) is a constant row, its soft-max is uniform and torch.max returns (1 / columns, 0); in every other row the
+    // padded columns underflow to exactly 0
+    const bool dead = m == -INFINITY || (p.mbits[dir] && !((p.mbits[dir][(size_t)b * p.mwords[dir] + (row >> 5)] >> (row & 31)) & 1u));
+    (dir ? conf10 : conf01)[i] = dead ? 1.0f / (float)p.L[1 - dir] : 1.0f / l;
+    (dir ? idx10 : idx01)[i] = dead ? 0 : arg;
+}
+
+// uint8 mask [B, L] -> one bit per token, 32 tokens per word: a warp per word
+__global__ void mask_pack_kernel(const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits, int B, int L, int words) {
+    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)B * words) return;
+    const int b = (int)(w / words), tok = (int)(w % words) * 32 + lane;
+    const unsigned bal = __ballot_sync(FULL_MASK, tok < L && mask[(size_t)b * L + tok] != 0);
+    if (lane == 0) bits[w] = bal;
 }
 
 int make_map3(CUtensorMap *tm, const float *base, int B, int L, int C, int rows) {
@@ -275,10 +294,13 @@ size_t coarse_match_workspace(int B, int L0, int L1, int C) {
     ws.take<float>((size_t)2 * ns * B * Lmax);
     ws.take<float>((size_t)2 * ns * B * Lmax);
     ws.take<int>((size_t)2 * ns * B * Lmax);
+    ws.take<uint32_t>((size_t)B * ((L0 + 31) / 32));
+    ws.take<uint32_t>((size_t)B * ((L1 + 31) / 32));
     return ws.off;
 }
 
-int launch_coarse_match(const float *feat0, const float *feat1, float temperature, float *conf01, int64_t *idx01, float *conf10,
+int launch_coarse_match(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1, float temperature,
+                        float *conf01, int64_t *idx01, float *conf10,
                         int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     CASMTR_REQUIRE(C % BK == 0 && C >= BK, CASMTR_E_UNSUPPORTED, "coarse_match: C=%d must be a multiple of %d", C, BK);
     CASMTR_REQUIRE((((uintptr_t)feat0 | (uintptr_t)feat1) & 15) == 0, CASMTR_E_INVALID, "coarse_match: features must be 16-byte aligned");
@@ -289,9 +311,19 @@ int launch_coarse_match(const float *feat0, const float *feat1, float temperatur
     p.pmax = ws.take<float>((size_t)2 * ns * B * Lmax);
     p.psum = ws.take<float>((size_t)2 * ns * B * Lmax);
     p.parg = ws.take<int>((size_t)2 * ns * B * Lmax);
+    uint32_t *bits0 = ws.take<uint32_t>((size_t)B * ((L0 + 31) / 32)), *bits1 = ws.take<uint32_t>((size_t)B * ((L1 + 31) / 32));
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "coarse_match: workspace %zu < %zu bytes", workspace_bytes, ws.off);
     p.B = B; p.L[0] = L0; p.L[1] = L1; p.C = C; p.nsplit = ns; p.Lmax = Lmax;
     p.scale_log2 = LOG2E_F / ((float)C * temperature);
+    p.mbits[0] = p.mbits[1] = nullptr;
+    p.mwords[0] = (L0 + 31) / 32; p.mwords[1] = (L1 + 31) / 32;
+    if (mask0 != nullptr) {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        mask_pack_kernel<<<(unsigned)(((size_t)B * p.mwords[0] * 32 + 255) / 256), 256, 0, stream>>>(mask0, bits0, B, L0, p.mwords[0]);
+        mask_pack_kernel<<<(unsigned)(((size_t)B * p.mwords[1] * 32 + 255) / 256), 256, 0, stream>>>(mask1, bits1, B, L1, p.mwords[1]);
+        CASMTR_CHECK_LAUNCH("mask_pack_kernel");
+        p.mbits[0] = bits0; p.mbits[1] = bits1;
+    }
     {
         LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
         tf32_residual_kernel<<<148 * 8, 256, 0, stream>>>((const float4 *)feat0, (float4 *)lo0, (size_t)B * L0 * C / 4);

@@ -363,21 +363,30 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
     return o
 
 
-def coarse_match_forward(feat0, feat1, temperature=0.1):
+def coarse_match_forward(feat0, feat1, temperature=0.1, mask0=None, mask1=None):
     """Dense dual-softmax statistics (tcgen05): feat0 [B,L0,C], feat1 [B,L1,C] -> dict next_conf01 [B,L0], next_idx01 [B,L0]
-    (int64), next_conf10 [B,L1], next_idx10 [B,L1]; the L0 x L1 similarity matrix is never materialised."""
+    (int64), next_conf10 [B,L1], next_idx10 [B,L1]; the L0 x L1 similarity matrix is never materialised.
+    mask0 [B,L0] / mask1 [B,L1] (bool, both or neither): padding masks as in the reference's masked_fill_(-1e9) (padded rows: uniform soft-max, i.e. 1 / columns and index 0)."""
     _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
     B, L0, Cc = feat0.shape
     L1 = feat1.shape[1]
     dev = feat0.device
+    if (mask0 is None) != (mask1 is None):
+        raise RuntimeError('give both masks or neither')
+    if mask0 is not None:
+        if mask0.shape != (B, L0) or mask1.shape != (B, L1):
+            raise RuntimeError(f'masks must be [B,L0] / [B,L1], got {tuple(mask0.shape)} / {tuple(mask1.shape)}')
+        mask0 = _chk((mask0 != 0).to(torch.uint8).contiguous(), 'mask0', torch.uint8)
+        mask1 = _chk((mask1 != 0).to(torch.uint8).contiguous(), 'mask1', torch.uint8)
     o = {'next_conf01': torch.empty(B, L0, dtype=torch.float32, device=dev), 'next_idx01': torch.empty(B, L0, dtype=torch.int64, device=dev),
          'next_conf10': torch.empty(B, L1, dtype=torch.float32, device=dev), 'next_idx10': torch.empty(B, L1, dtype=torch.int64, device=dev)}
     with torch.cuda.device(dev):
         nbytes = lib().casmtr_coarse_match_workspace_bytes(B, L0, L1, Cc)
         ws = _workspace(nbytes, dev)
-        check(lib().casmtr_coarse_match_fwd(_ptr(feat0), _ptr(feat1), float(temperature), _ptr(o['next_conf01']), _ptr(o['next_idx01']),
-                                            _ptr(o['next_conf10']), _ptr(o['next_idx10']), B, L0, L1, Cc, _ptr(ws), ws.numel(),
-                                            _stream(feat0)), 'casmtr_coarse_match_fwd')
+        check(lib().casmtr_coarse_match_masked_fwd(_ptr(feat0), _ptr(feat1), _ptr(mask0), _ptr(mask1), float(temperature),
+                                                   _ptr(o['next_conf01']), _ptr(o['next_idx01']),
+                                                   _ptr(o['next_conf10']), _ptr(o['next_idx10']), B, L0, L1, Cc, _ptr(ws), ws.numel(),
+                                                   _stream(feat0)), 'casmtr_coarse_match_masked_fwd')
     return o
 
 

@@ -272,6 +272,14 @@ CASMTR_API size_t casmtr_coarse_match_workspace_bytes(int B, int L0, int L1, int
 CASMTR_API int casmtr_coarse_match_fwd(const float *feat0, const float *feat1, float temperature,
                             float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
                             int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+/* With the padding masks of the two images (reference :64-65, sim.masked_fill_(~(mask0[:, :, None] * mask1[:, None]), -INF)):
+ * mask0 [B,L0], mask1 [B,L1] uint8 (the reference's bool tensors; both or neither NULL).  Padded columns take no part in the
+ * row soft-max / arg-max (exp(-1e9 - max) is exactly 0 in fp32); a padded row is constant (-INF is -1e9 there, :6), so its
+ * soft-max is uniform: next_conf = 1 / columns, next_idx = 0, as torch.max returns.  Same workspace. */
+CASMTR_API int casmtr_coarse_match_masked_fwd(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1,
+                            float temperature,
+                            float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                            int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS + match extraction (R7) */
 

@@ -13,11 +13,14 @@ import torch.nn.functional as tF
 from . import qtatt
 
 
-def coarse_match_stats(feat0, feat1, temperature, dtype=torch.float32):
+def coarse_match_stats(feat0, feat1, temperature, dtype=torch.float32, mask0=None, mask1=None):
     """feat0 [B,L,C], feat1 [B,S,C] -> next_conf01 [B,L], next_idx01 [B,L], next_conf10 [B,S], next_idx10 [B,S] and the
-    dense similarity (for tie analysis).  :60 normalise, :63 einsum / T, :66-67 the two softmaxes, :70-71 max."""
+    dense similarity (for tie analysis).  :60 normalise, :63 einsum / T, :64-65 padding masks (bool [B,L] / [B,S]) filled with
+    -INF = -1e9 (:9), :66-67 the two softmaxes, :70-71 max."""
     C = feat0.shape[-1]
     sim = torch.einsum('nlc,nsc->nls', feat0.to(dtype) / C ** 0.5, feat1.to(dtype) / C ** 0.5) / temperature
+    if mask0 is not None:
+        sim = sim.masked_fill(~(mask0[..., None] * mask1[:, None]).bool(), -1e9)
     p10, p01 = torch.softmax(sim, 1), torch.softmax(sim, 2)
     c01, i01 = p01.max(dim=2)
     c10, i10 = p10.max(dim=1)

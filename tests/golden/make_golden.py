@@ -231,6 +231,33 @@ def gen_widen(ref):
          cas_x=xc, cas_target=tc, cas_topk_pos=d['topk_pos01'], cas_out=co, cas_upsampled_idx=cup, **out)
 
 
+def gen_coarse_match_masked(ref):
+    """The reference's CoarseMatching with padding masks (mask_c0 / mask_c1, coarse_matching.py:64-65): bottom / right bands of
+    the 1/8 grids padded, differently per image and batch element."""
+    import importlib
+    g = torch.Generator().manual_seed(31)
+    cmod = importlib.import_module('src.model.functions.coarse_matching')
+    B, h, w, C = 2, 12, 16, 64
+    f0 = torch.randn(B, h * w, C, generator=g)
+    f1 = 0.8 * f0[:, torch.randperm(h * w, generator=g)] + 0.6 * torch.randn(B, h * w, C, generator=g)
+
+    def band_mask(valid):
+        m = torch.zeros(B, h, w, dtype=torch.bool)
+        for b, (vh, vw) in enumerate(valid):
+            m[b, :vh, :vw] = True
+        return m.reshape(B, h * w)
+    m0, m1 = band_mask([(10, 16), (12, 11)]), band_mask([(12, 13), (9, 16)])
+    cfg = {'thr': 0.2, 'border_rm': 2, 'train_coarse_percent': 0.3, 'train_pad_num_gt_min': 200, 'match_type': 'dual_softmax',
+           'dsmax_temperature': 0.1}
+    data = {'hw0_i': (h * 8, w * 8), 'hw1_i': (h * 8, w * 8), 'hw0_8c': (h, w), 'hw1_8c': (h, w), 'bs': B}
+    m = cmod.CoarseMatching(cfg).eval()
+    with torch.no_grad():
+        m(f0, f1, data, mask_c0=m0, mask_c1=m1)
+    st = data['stage_8c']
+    save('widen_coarse_match_masked', feat0=f0, feat1=f1, mask0=m0, mask1=m1, temperature=torch.tensor(0.1),
+         next_conf01=st['next_conf_c01'], next_idx01=st['next_idx_c01'], next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'])
+
+
 def gen_relative_pe(ref):
     """get_window_warp_idx + get_relative_pe of the reference's CascadeFeatureTransformer, unbound on a stand-in that carries
     what they read (window, LB, the two nn.Embedding tables), followed by the reference's CascadeQTAttB with that bias.
@@ -302,4 +329,5 @@ if __name__ == '__main__':
     gen_fine(ref)
     gen_windows(ref)
     gen_widen(ref)
+    gen_coarse_match_masked(ref)
     gen_relative_pe(ref)

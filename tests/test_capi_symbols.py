@@ -63,6 +63,9 @@ def test_argument_validation_of_the_widening_entries():
     assert lib.casmtr_fine_match_dev_fwd(None, None, None, None, None, 1.0, None, None, None, 8, 25, 64, None) == -1    # no count
     assert lib.casmtr_pack_matches_dev(None, None, None, None, None, None, None, 0, 8, None, None) == -1
     assert lib.casmtr_coarse_match_workspace_bytes(1, 0, 16, 256) == 0
+    one8 = ctypes.cast(ctypes.pointer(ctypes.c_float(0)), ctypes.c_void_p)
+    rc = lib.casmtr_coarse_match_masked_fwd(one8, one8, one8, None, 0.1, one8, one8, one8, one8, 1, 64, 64, 64, one8, 1 << 20, None)
+    assert rc == -1 and b'both masks' in lib.casmtr_last_error_string()
     d = _lib.QtattDesc()
     d.B, d.nhead, d.D, d.levels, d.type = 1, 2, 32, 2, 0
     d.qh[0] = d.qw[0] = d.kh[0] = d.kw[0] = 16

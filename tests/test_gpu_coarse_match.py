@@ -51,3 +51,56 @@ def test_coarse_matching_module(dev):
     st = data['stage_8c']
     assert torch.equal(st['next_idx_c01'].cpu()[g01 > 1e-4], i01[g01 > 1e-4]) and (st['next_conf_c10'].cpu() - c10).abs().max() < 1e-3
     assert st['conf_matrix'] is None
+
+
+# ---- padding masks (reference coarse_matching.py:64-65: masked_fill_ with -INF = -1e9)
+def test_coarse_match_masked_golden(dev):
+    """Against the reference's own CoarseMatching run with mask_c0 / mask_c1 (tests/golden/make_golden.py): indices bit-exact
+    (padded rows: 0), confidences within 1e-3 (padded rows: the uniform 1 / columns)."""
+    from golden_util import load
+    g = load('widen_coarse_match_masked')
+    m0, m1 = g['mask0'].bool(), g['mask1'].bool()
+    o = F.coarse_match_forward(g['feat0'].to(dev), g['feat1'].to(dev), float(g['temperature']), m0.to(dev), m1.to(dev))
+    assert torch.equal(o['next_idx01'].cpu(), g['next_idx01']) and torch.equal(o['next_idx10'].cpu(), g['next_idx10'])
+    assert (o['next_conf01'].cpu() - g['next_conf01']).abs().max() < 1e-3 and (o['next_conf10'].cpu() - g['next_conf10']).abs().max() < 1e-3
+    assert torch.equal(o['next_conf01'].cpu()[~m0], g['next_conf01'][~m0])          # 1 / 192 exactly
+
+
+@pytest.mark.parametrize('B,hw0,valid0,hw1,valid1,C', [(1, (104, 104), (104, 78), (104, 104), (69, 104), 256),     # 832^2, MegaDepth-style bands
+                                                       (2, (20, 30), (13, 30), (24, 18), (24, 18), 64)])
+def test_coarse_match_masked_equals_the_valid_sub_problem(dev, B, hw0, valid0, hw1, valid1, C):
+    """Size-independent property: with band masks the statistics of the valid rows must equal those of the dense problem on
+    the gathered valid tokens (same kernel, no masks), indices mapped back; padded rows are (1 / columns, 0)."""
+    g = torch.Generator().manual_seed(hw0[0] + hw1[1])
+    L0, L1 = hw0[0] * hw0[1], hw1[0] * hw1[1]
+    f0, f1 = torch.randn(B, L0, C, generator=g).to(dev), torch.randn(B, L1, C, generator=g).to(dev)
+
+    def band(hw, valid):
+        m = torch.zeros(hw, dtype=torch.bool)
+        m[:valid[0], :valid[1]] = True
+        return m.reshape(-1)
+    v0, v1 = band(hw0, valid0).to(dev), band(hw1, valid1).to(dev)
+    o = F.coarse_match_forward(f0, f1, 0.1, v0[None].expand(B, -1), v1[None].expand(B, -1))
+    sub = F.coarse_match_forward(f0[:, v0].contiguous(), f1[:, v1].contiguous(), 0.1)
+    id0, id1 = torch.nonzero(v0).flatten(), torch.nonzero(v1).flatten()
+    assert torch.equal(o['next_idx01'][:, v0], id1[sub['next_idx01']]) and torch.equal(o['next_idx10'][:, v1], id0[sub['next_idx10']])
+    assert (o['next_conf01'][:, v0] - sub['next_conf01']).abs().max() < 1e-6 and (o['next_conf10'][:, v1] - sub['next_conf10']).abs().max() < 1e-6
+    if (~v0).any():
+        assert (o['next_idx01'][:, ~v0] == 0).all() and (o['next_conf01'][:, ~v0] == 1.0 / L1).all()
+    if (~v1).any():
+        assert (o['next_idx10'][:, ~v1] == 0).all() and (o['next_conf10'][:, ~v1] == 1.0 / L0).all()
+
+
+def test_coarse_matching_module_with_masks(dev):
+    import casmtr_b200
+    from golden_util import load
+    g = load('widen_coarse_match_masked')
+    cfg = {'thr': 0.2, 'border_rm': 2, 'match_type': 'dual_softmax', 'dsmax_temperature': float(g['temperature']), 'train_coarse_percent': 0.3,
+           'train_pad_num_gt_min': 200}
+    data = {}
+    mod = casmtr_b200.CoarseMatching(cfg).eval()
+    mod(g['feat0'].to(dev), g['feat1'].to(dev), data, mask_c0=g['mask0'].bool().to(dev), mask_c1=g['mask1'].bool().to(dev))
+    st = data['stage_8c']
+    assert torch.equal(st['next_idx_c01'].cpu(), g['next_idx01']) and torch.equal(st['next_idx_c10'].cpu(), g['next_idx10'])
+    with pytest.raises(RuntimeError):
+        mod(g['feat0'].to(dev), g['feat1'].to(dev), data, mask_c0=g['mask0'].bool().to(dev))
