@@ -1,5 +1,5 @@
 // extern "C" entry points of libcasmtr_b200.so (see include/casmtr_b200.h): argument validation,
-// workspace carving and kernel sequencing.  No allocation, no synchronisation, caller's stream.
+// workspace carving and kernel sequencing.  No allocation, no synchronisation, caller's stream (plus the fork/join side lanes below).
 #include <cstdlib>
 #include <stdarg.h>
 #include <string.h>

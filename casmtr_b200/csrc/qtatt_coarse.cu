@@ -19,6 +19,13 @@
 //            yields the list sorted descending like torch.topk(sorted=True) (ties: lower key index first).
 //   phase 4  O = A V, lane = query row again (32 accumulators in registers), V tile broadcast from smem,
 //            warps split the tokens, partial sums reduced across warps through smem.
+//
+// Why the two contractions stay on FFMA2 (instruction count per 16-row CTA, Sk = 676, 11 tiles):
+//   now      phase 1: per warp and tile 4 tokens x (8 LDS.128 + 16 FFMA2) + 4 stores ~ 110 instructions; phase 4 about the same
+//            -> ~19 K of the CTA's ~82 K instructions (ncu smsp__inst_executed / 344 CTAs); the soft-max + exact top-k is ~37 K.
+//   mma.sync m16n8k8 with a 3-term TF32 split (needed for fp32-exact top-k): per warp and tile 4 k-steps x (2 LDS + 6 split
+//            ALU + 3 MMA) = 44 (phase 1) and ~60 (phase 4) -> ~9 K.  Saves ~10 K of 82 K = 12 % of this kernel, ~2.5 % of a step;
+//            tcgen05 needs M >= 64 rows per CTA, i.e. 88 CTAs for 148 SMs while the soft-max / top-k part needs every SM.
 #include <cuda_pipeline.h>
 
 #include "common.cuh"

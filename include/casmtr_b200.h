@@ -7,7 +7,8 @@
  *   - every pointer is a DEVICE pointer unless stated otherwise; all tensors are dense,
  *     row-major, fp32 / int64 exactly as the reference's Python modules hand them over;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every
- *     launch goes to that stream, nothing synchronises;
+ *     launch goes to that stream (or, inside casmtr_qtatt_fwd, to a side stream forked from and
+ *     joined back into it -- see casmtr_set_overlap), nothing synchronises;
  *   - return value 0 = success, <0 = error (see CASMTR_E_*); the message of the last error
  *     on the calling thread is returned by casmtr_last_error_string();
  *   - no allocation inside the library: fused entry points take a caller-owned workspace
