@@ -49,6 +49,9 @@ SIGNATURES = {
     'casmtr_score5d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_value_agg_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_score3d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'casmtr_score5d_bwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
+    'casmtr_value_agg_bwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
+    'casmtr_score3d_bwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p] + [C.c_int] * 5 + [C.c_void_p]),
     'casmtr_nchw_to_tokens': (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'casmtr_qtatt_workspace_bytes': (C.c_size_t, [C.POINTER(QtattDesc)]),
     'casmtr_qtatt_fwd': (C.c_int, [C.POINTER(QtattDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -17,11 +17,14 @@ class ScoreComputation(torch.autograd.Function):
     @staticmethod
     def forward(ctx, query, key, index):
         # the reference's launch-geometry guards (:11-12) do not apply to this kernel and are lifted
+        ctx.save_for_backward(query, key, index)
         return F.score3d(query, key, index)
 
     @staticmethod
-    def backward(ctx, grad_output):
-        raise NotImplementedError('casmtr_b200 implements the inference (forward) path only')
+    def backward(ctx, grad_output):                                      # reference :17-22
+        query, key, index = ctx.saved_tensors
+        gq, gk = F.score3d_backward(grad_output.contiguous(), query, key, index)
+        return gq, gk, None
 
 
 class PostProcess(object):

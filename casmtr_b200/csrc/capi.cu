@@ -201,6 +201,30 @@ int casmtr_nchw_to_tokens(const float *src, float *dst, int B, int C, int HW, ca
     return launch_transpose_jobs(jobs, B, (cudaStream_t)stream);
 }
 
+int casmtr_score5d_bwd(const float *grad_out, const float *query, const float *key, const int64_t *index,
+                       float *grad_query, float *grad_key, int B, int N1, int N2, int H, int D, int K, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N1 >= 0 && N2 > 0 && H > 0 && D > 0 && K > 0, CASMTR_E_INVALID, "score5d_bwd: bad sizes");
+    CASMTR_REQUIRE(grad_key != nullptr || B == 0, CASMTR_E_INVALID, "score5d_bwd: null grad_key");
+    CASMTR_REQUIRE((grad_out && query && key && index && grad_query) || (size_t)B * N1 == 0, CASMTR_E_INVALID, "score5d_bwd: null pointer");
+    return launch_score5d_bwd(grad_out, query, key, index, grad_query, grad_key, B, N1, N2, H, D, K, (cudaStream_t)stream);
+}
+
+int casmtr_value_agg_bwd(const float *grad_out, const float *score, const float *value, const int64_t *index,
+                         float *grad_score, float *grad_value, int B, int N, int K, int H, int M, int D, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N >= 0 && K > 0 && H > 0 && M > 0 && D > 0, CASMTR_E_INVALID, "value_agg_bwd: bad sizes");
+    CASMTR_REQUIRE(grad_value != nullptr || B == 0, CASMTR_E_INVALID, "value_agg_bwd: null grad_value");
+    CASMTR_REQUIRE((grad_out && score && value && index && grad_score) || (size_t)B * N == 0, CASMTR_E_INVALID, "value_agg_bwd: null pointer");
+    return launch_value_agg_bwd(grad_out, score, value, index, grad_score, grad_value, B, N, K, H, M, D, (cudaStream_t)stream);
+}
+
+int casmtr_score3d_bwd(const float *grad_out, const float *query, const float *key, const int64_t *index,
+                       float *grad_query, float *grad_key, int B, int N1, int N2, int C, int K, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 0 && N1 >= 0 && N2 > 0 && C > 0 && K > 0, CASMTR_E_INVALID, "score3d_bwd: bad sizes");
+    CASMTR_REQUIRE(grad_key != nullptr || B == 0, CASMTR_E_INVALID, "score3d_bwd: null grad_key");
+    CASMTR_REQUIRE((grad_out && query && key && index && grad_query) || (size_t)B * N1 == 0, CASMTR_E_INVALID, "score3d_bwd: null pointer");
+    return launch_score3d_bwd(grad_out, query, key, index, grad_query, grad_key, B, N1, N2, C, K, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ QTAtt
 static int check_qtatt_desc(const casmtr_qtatt_desc *d) {
     CASMTR_REQUIRE(d != nullptr, CASMTR_E_INVALID, "qtatt: null descriptor");

@@ -119,6 +119,14 @@ int launch_value_agg(const float *score, const float *value, const int64_t *idx,
 int launch_score3d(const float *q, const float *key, const int64_t *idx, float *out,
                    int B, int N1, int N2, int C, int K, cudaStream_t stream);
 
+// ---- ops_bwd.cu: backward halves of the three op-level drop-ins (grad_key / grad_value are zeroed inside)
+int launch_score5d_bwd(const float *grad, const float *q, const float *key, const int64_t *idx, float *gq, float *gk,
+                       int B, int N1, int N2, int H, int D, int K, cudaStream_t stream);
+int launch_value_agg_bwd(const float *grad, const float *score, const float *value, const int64_t *idx, float *gscore, float *gvalue,
+                         int B, int N, int K, int H, int M, int D, cudaStream_t stream);
+int launch_score3d_bwd(const float *grad, const float *q, const float *key, const int64_t *idx, float *gq, float *gk,
+                       int B, int N1, int N2, int C, int K, cudaStream_t stream);
+
 // ---- cascade_match.cu
 struct MatchParams {
     const float *feat0, *feat1;

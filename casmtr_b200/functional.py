@@ -106,6 +106,51 @@ def score3d(query, key, index):
     return out
 
 
+def score5d_backward(grad_output, query, key, index):
+    """-> (grad_query [B,N1,4,H,D], grad_key [B,N2,H,D]) of score5d for grad_output [B,N1,4,K,H]."""
+    _chk(grad_output, 'grad_output', torch.float32), _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32)
+    _chk(index, 'index', torch.int64)
+    B, N1, _, H, D = query.shape
+    N2, K = key.shape[1], index.shape[2]
+    if grad_output.shape != (B, N1, 4, K, H):
+        raise RuntimeError(f'grad_output must be [B,N1,4,K,H], got {tuple(grad_output.shape)}')
+    gq, gk = torch.empty_like(query), torch.empty_like(key)
+    with torch.cuda.device(query.device):
+        check(lib().casmtr_score5d_bwd(_ptr(grad_output), _ptr(query), _ptr(key), _ptr(index), _ptr(gq), _ptr(gk), B, N1, N2, H, D, K,
+                                       _stream(query)), 'casmtr_score5d_bwd')
+    return gq, gk
+
+
+def value_agg_backward(grad_output, score, value, index):
+    """-> (grad_score [B,N,K,H], grad_value [B,M,H,D]) of value_agg for grad_output [B,N,H,D]."""
+    _chk(grad_output, 'grad_output', torch.float32), _chk(score, 'score', torch.float32), _chk(value, 'value', torch.float32)
+    _chk(index, 'index', torch.int64)
+    B, N, K, H = score.shape
+    M, D = value.shape[1], value.shape[3]
+    if grad_output.shape != (B, N, H, D):
+        raise RuntimeError(f'grad_output must be [B,N,H,D], got {tuple(grad_output.shape)}')
+    gs, gv = torch.empty_like(score), torch.empty_like(value)
+    with torch.cuda.device(score.device):
+        check(lib().casmtr_value_agg_bwd(_ptr(grad_output), _ptr(score), _ptr(value), _ptr(index), _ptr(gs), _ptr(gv), B, N, K, H, M, D,
+                                         _stream(score)), 'casmtr_value_agg_bwd')
+    return gs, gv
+
+
+def score3d_backward(grad_output, query, key, index):
+    """-> (grad_query [B,N1,C], grad_key [B,N2,C]) of score3d for grad_output [B,N1,K]."""
+    _chk(grad_output, 'grad_output', torch.float32), _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32)
+    _chk(index, 'index', torch.int64)
+    B, N1, Cc = query.shape
+    N2, K = key.shape[1], index.shape[2]
+    if grad_output.shape != (B, N1, K):
+        raise RuntimeError(f'grad_output must be [B,N1,K], got {tuple(grad_output.shape)}')
+    gq, gk = torch.empty_like(query), torch.empty_like(key)
+    with torch.cuda.device(query.device):
+        check(lib().casmtr_score3d_bwd(_ptr(grad_output), _ptr(query), _ptr(key), _ptr(index), _ptr(gq), _ptr(gk), B, N1, N2, Cc, K,
+                                       _stream(query)), 'casmtr_score3d_bwd')
+    return gq, gk
+
+
 def nchw_to_tokens(x):
     _chk(x, 'x', torch.float32)
     B, Cc = x.shape[:2]

@@ -8,4 +8,5 @@ def score_forward(query, key, index):
 
 
 def score_backward(grad_output, query, key, index):
-    raise NotImplementedError('casmtr_b200 implements the inference (forward) path only')
+    """-> [grad_query [B,N1,C], grad_key [B,N2,C]] (reference score_cuda/src/score_computation.cpp:19-27)"""
+    return list(_F.score3d_backward(grad_output, query, key, index))

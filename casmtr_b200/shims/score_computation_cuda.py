@@ -9,4 +9,5 @@ def score_forward(query, key, index):
 
 
 def score_backward(grad_output, query, key, index):
-    raise NotImplementedError('casmtr_b200 implements the inference (forward) path only')
+    """-> [grad_query [B,N1,4,H,D], grad_key [B,N2,H,D]] (reference score_computation.cpp:22-33)"""
+    return list(_F.score5d_backward(grad_output, query, key, index))

@@ -9,4 +9,8 @@ def value_aggregation_forward(score, value, index, output):
 
 
 def value_aggregation_backward(grad_output, score, value, index, grad_score, grad_value):
-    raise NotImplementedError('casmtr_b200 implements the inference (forward) path only')
+    """ACCUMULATES into the caller's grad_score [B,N,K,H] / grad_value [B,M,H,D] like the reference kernel (which the
+    reference wrapper hands zero-filled tensors, functions/quadtree_attention.py:47-48)."""
+    gs, gv = _F.value_agg_backward(grad_output, score, value, index)
+    grad_score.add_(gs)
+    grad_value.add_(gv)

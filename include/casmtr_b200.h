@@ -107,6 +107,21 @@ CASMTR_API int casmtr_value_agg_fwd(const float *score, const float *value, cons
 CASMTR_API int casmtr_score3d_fwd(const float *query, const float *key, const int64_t *index, float *out,
                        int B, int N1, int N2, int C, int K, casmtr_stream_t stream);
 
+/* Backward halves of the three ops (SURVEY 8f "next" #4; reference score_computation.cpp:22-33 `score_backward`,
+ * value_aggregation.cpp:33-60 `value_aggregation_backward`, score_cuda/src/score_computation.cpp:19-27 `score_backward`), so
+ * that the reference's autograd Functions train on this library.  Tensor contracts as in the forward calls.  grad_query /
+ * grad_score are fully written (no atomics); grad_key / grad_value are zeroed here and then accumulated with 16-byte vector
+ * reductions -- reproducible to fp32 rounding of the sum, not bit for bit (the reference's scalar atomicAdd is the same).
+ *   score5d:   grad_out [B,N1,4,K,H] -> grad_query [B,N1,4,H,D], grad_key [B,N2,H,D]        D % 4 == 0, H*D <= 1024
+ *   value_agg: grad_out [B,N,H,D]    -> grad_score [B,N,K,H],   grad_value [B,M,H,D]        D in {4,..,128} power of two
+ *   score3d:   grad_out [B,N1,K]     -> grad_query [B,N1,C],    grad_key [B,N2,C]           C % 4 == 0, C <= 512 */
+CASMTR_API int casmtr_score5d_bwd(const float *grad_out, const float *query, const float *key, const int64_t *index,
+                       float *grad_query, float *grad_key, int B, int N1, int N2, int H, int D, int K, casmtr_stream_t stream);
+CASMTR_API int casmtr_value_agg_bwd(const float *grad_out, const float *score, const float *value, const int64_t *index,
+                         float *grad_score, float *grad_value, int B, int N, int K, int H, int M, int D, casmtr_stream_t stream);
+CASMTR_API int casmtr_score3d_bwd(const float *grad_out, const float *query, const float *key, const int64_t *index,
+                       float *grad_query, float *grad_key, int B, int N1, int N2, int C, int K, casmtr_stream_t stream);
+
 /* NCHW -> token-major: src [B,C,HW] -> dst [B,HW,C] (exported for tests / callers that want
  * to keep features token-major between layers). */
 CASMTR_API int casmtr_nchw_to_tokens(const float *src, float *dst, int B, int C, int HW, casmtr_stream_t stream);

@@ -110,3 +110,47 @@ def test_reference_data_flow_restated(dev, ref):
     wm, wu = oqt.cascade_qtatt_b(d['feat0'], d['feat1'], v, d['topk_pos01'], None, nh)
     gm, gu = ref_path.cascade_qtatt_b(d['feat0'].to(dev), d['feat1'].to(dev), v.to(dev), d['topk_pos01'].to(dev), nh)
     assert torch.equal(gu.cpu(), wu) and (gm.cpu() - wm).abs().max() < 1e-4
+
+
+# ---- backward halves against the reference's own backward kernels (score_backward / value_aggregation_backward)
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize('B,N1,N2,H,D,K', [(2, 12, 48, 4, 32, 20), (1, 169, 676, 8, 32, 128)])
+def test_score5d_backward_vs_reference_kernel(dev, ref, B, N1, N2, H, D, K):
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, N1, 4, H, D, generator=g).to(dev)
+    k = torch.randn(B, N2, H, D, generator=g).to(dev)
+    idx = torch.randint(0, N2, (B, N1, K, H), generator=g).to(dev)
+    go = torch.randn(B, N1, 4, K, H, generator=g).to(dev)
+    wq, wk = ref['score_computation_cuda'].score_backward(go, q, k, idx)
+    torch.cuda.synchronize()
+    gq, gk = F.score5d_backward(go, q, k, idx)
+    assert _rel(gq, wq) < 1e-5 and _rel(gk, wk) < 1e-5
+
+
+@pytest.mark.parametrize('B,N,K,H,M,D', [(2, 40, 16, 4, 50, 32), (1, 676, 64, 8, 676, 32)])
+def test_value_agg_backward_vs_reference_kernel(dev, ref, B, N, K, H, M, D):
+    g = torch.Generator().manual_seed(12)
+    s = torch.rand(B, N, K, H, generator=g).to(dev)
+    v = torch.randn(B, M, H, D, generator=g).to(dev)
+    idx = torch.randint(0, M, (B, N, K, H), generator=g).to(dev)
+    go = torch.randn(B, N, H, D, generator=g).to(dev)
+    ws, wv = torch.zeros_like(s), torch.zeros_like(v)
+    ref['value_aggregation_cuda'].value_aggregation_backward(go, s, v, idx, ws, wv)
+    gs, gv = F.value_agg_backward(go, s, v, idx)
+    assert _rel(gs, ws) < 1e-5 and _rel(gv, wv) < 1e-5
+
+
+@pytest.mark.parametrize('B,N1,N2,C,K', [(2, 48, 50, 64, 10), (1, 1024, 1024, 128, 100)])
+def test_score3d_backward_vs_reference_kernel(dev, ref, B, N1, N2, C, K):
+    g = torch.Generator().manual_seed(13)
+    q = torch.randn(B, N1, C, generator=g).to(dev)
+    k = torch.randn(B, N2, C, generator=g).to(dev)
+    idx = torch.randint(0, N2, (B, N1, K), generator=g).to(dev)
+    go = torch.randn(B, N1, K, generator=g).to(dev)
+    wq, wk = ref['fast_score_computation'].score_backward(go, q, k, idx)
+    torch.cuda.synchronize()
+    gq, gk = F.score3d_backward(go, q, k, idx)
+    assert _rel(gq, wq) < 1e-5 and _rel(gk, wk) < 1e-5
