@@ -507,6 +507,39 @@ def run_ours(args):
                         '(casmtr_relative_pe_fwd; ~25 torch ops in the reference) and read by the attention kernels, vs computed inside them '
                         'from the two embedding tables (casmtr_cascade_qtatt_relpe_fwd)'}
             del rp
+            # "next" #4, second half: backward of the three op-level drop-ins at the shapes of the hot path, next to the
+            # reference's own backward kernels (oracle/_ref, built unmodified) where they are available
+            g = torch.Generator().manual_seed(10)
+            L2q, L2k = (wl.h8 // 2) * (wl.w8 // 2), wl.h8 * wl.w8                 # last QTAttB level: parents, keys
+            q5 = torch.randn(wl.B, L2q, 4, wl.nh8, 32, generator=g).to(dev)
+            k5 = torch.randn(wl.B, L2k, wl.nh8, 32, generator=g).to(dev)
+            i5 = torch.randint(0, L2k, (wl.B, L2q, 4 * wl.topks[1], wl.nh8), generator=g).to(dev)
+            go5 = torch.randn(wl.B, L2q, 4, 4 * wl.topks[1], wl.nh8, generator=g).to(dev)
+            s5 = torch.rand(wl.B, 4 * L2q, 4 * wl.topks[1], wl.nh8, generator=g).to(dev)
+            i5v = i5.view(wl.B, L2q, 1, -1, wl.nh8).expand(-1, -1, 4, -1, -1).reshape(wl.B, 4 * L2q, -1, wl.nh8).contiguous()
+            gov = torch.randn(wl.B, 4 * L2q, wl.nh8, 32, generator=g).to(dev)
+            L4 = wl.h4 * wl.w4
+            q3, k3 = torch.randn(wl.B, L4, wl.C4, generator=g).to(dev), torch.randn(wl.B, L4, wl.C4, generator=g).to(dev)
+            i3 = torch.randint(0, L4, (wl.B, L4, 100), generator=g).to(dev)
+            go3 = torch.randn(wl.B, L4, 100, generator=g).to(dev)
+            ob = {'ms_score5d_bwd': _time(lambda: F.score5d_backward(go5, q5, k5, i5), n=10),
+                  'ms_value_agg_bwd': _time(lambda: F.value_agg_backward(gov, s5, k5, i5v), n=10),
+                  'ms_score3d_bwd': _time(lambda: F.score3d_backward(go3, q3, k3, i3), n=10),
+                  'shapes': {'score5d': [wl.B, L2q, L2k, wl.nh8, 32, 4 * wl.topks[1]], 'value_agg': [wl.B, 4 * L2q, 4 * wl.topks[1], wl.nh8, L2k, 32],
+                             'score3d': [wl.B, L4, L4, wl.C4, 100]},
+                  'what': 'backward of score5d / value_agg at the last QTAttB level and of score3d at the 1/4 cascade level (random indices), '
+                          'this library vs the reference kernels (scalar atomicAdd per element) on the same GPU'}
+            try:
+                from oracle import build_ref
+                if all(build_ref.built(n) for n in ('score_computation_cuda', 'value_aggregation_cuda', 'fast_score_computation')):
+                    r5, rv, r3 = (build_ref.load(n) for n in ('score_computation_cuda', 'value_aggregation_cuda', 'fast_score_computation'))
+                    ob['ms_score5d_bwd_reference'] = _time(lambda: r5.score_backward(go5, q5, k5, i5), n=5)
+                    ob['ms_value_agg_bwd_reference'] = _time(lambda: rv.value_aggregation_backward(gov, s5, k5, i5v, torch.zeros_like(s5), torch.zeros_like(k5)), n=5)
+                    ob['ms_score3d_bwd_reference'] = _time(lambda: r3.score_backward(go3, q3, k3, i3), n=3)
+            except Exception as e:      # noqa: BLE001
+                ob['reference_error'] = str(e)[:200]
+            next_rows['op_backward'] = ob
+            del q5, k5, i5, go5, s5, i5v, gov, q3, k3, i3, go3
             M = max(n_matches, 1)
             g = torch.Generator().manual_seed(9)
             ff = torch.randn(wl.B, 64, wl.hf, wl.wf, generator=g).to(dev)
