@@ -14,6 +14,9 @@ timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $O
 cat $OUT/${TAG}_bench.json | cut -c1-600
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
 cat $OUT/${TAG}_bench_ref.json | cut -c1-300
+# per-kernel counters: one transpose launch per call (CASMTR_OVERLAP=0) keeps the -s / -c launch arithmetic below simple; the
+# launch list above is taken with the library's defaults
+export CASMTR_OVERLAP=0
 BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $OUT/${TAG}_ncu_launch.log 2>&1
@@ -21,7 +24,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tra
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|cascade_att_tile|quad_attention_list' -s 12 -c 3 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_match|extract_|fine_match' -c 6 -f -o $OUT/${TAG}_match $BENCH > $OUT/${TAG}_ncu_c.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'coarse_rowstats|pool2_tokens|fine_window_gather|tf32_residual' -c 4 -f -o $OUT/${TAG}_widen $BENCH > $OUT/${TAG}_ncu_d.log 2>&1
-for r in qtatt cascade match widen; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'relative_pe_kernel|score5d_bwd_kernel|value_agg_bwd_kernel|score3d_bwd_kernel' -c 4 -f -o $OUT/${TAG}_widen2 $BENCH > $OUT/${TAG}_ncu_e.log 2>&1
+for r in qtatt cascade match widen widen2; do
   ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null
 done
 ls -la $OUT; du -sh $OUT

@@ -20,7 +20,8 @@ OUT, PROF = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 KIND = [('transpose_vec', 'layout'), ('qtatt_coarse', 'qt_coarse'), ('quad_cta', 'qt_fine_mid'), ('quad_attention_kernel', 'qt_fine_last'),
         ('cascade_att_tile', 'cascade_att'), ('quad_attention_list', 'cascade_fallback'), ('cascade_match_tile', 'cascade_match'),
         ('cascade_match_cell', 'cascade_match_fallback'), ('coarse_rowstats', 'coarse_match'), ('pool2_tokens', 'pool_tokens'),
-        ('fine_window_gather', 'fine_window_gather'), ('fine_match', 'fine_match'), ('extract_mask', 'extract')]
+        ('fine_window_gather', 'fine_window_gather'), ('fine_match', 'fine_match'), ('extract_mask', 'extract'),
+        ('relative_pe_kernel', 'relative_pe'), ('score5d_bwd', 'score5d_bwd'), ('value_agg_bwd', 'value_agg_bwd'), ('score3d_bwd', 'score3d_bwd')]
 
 
 def num(x):
@@ -48,7 +49,7 @@ def rows_of(path):
     return out
 
 
-raws = [os.path.join(OUT, f'{TAG}_{r}_raw.csv') for r in ('qtatt', 'cascade', 'match', 'widen')]
+raws = [os.path.join(OUT, f'{TAG}_{r}_raw.csv') for r in ('qtatt', 'cascade', 'match', 'widen', 'widen2')]
 raws = [p for p in raws if os.path.exists(p)]
 buf = io.StringIO()
 buf.write(f'# {TAG} -- B200, `ncu --set full --clock-control none --import-source on`, one launch per kernel\n'
