@@ -10,10 +10,12 @@ CascadeMatching (2 sparse correlations, softmax/argmax, 5x5 NMS, extraction) + C
 (casmtr_b200/pipeline.py).  A step = one pass of that sequence over one batch of synthetic feature maps.
 
   value      pairs/s with the step's inputs resident in HBM (every call has its own input buffers; one step
-             touches ~0.9 GB > the 126 MB L2, so nothing is served from a previous step's cache lines).  Two timed
-             passes of K steps each: an eager single-stream pass in which the library brackets every kernel with CUDA
-             events (breakdown / roofline, `value_eager_instrumented`), and the same step replayed as a CUDA graph with
-             the two independent directions of each layer on two streams; `value` is the faster of the two (`execution`)
+             touches ~0.9 GB > the 126 MB L2, so nothing is served from a previous step's cache lines).  Timed passes
+             of K steps each: an eager single-stream pass in which the library brackets every kernel with CUDA events
+             (breakdown / roofline, `value_eager_instrumented`), the same eager step without those events
+             (`ms_per_step_eager`, and `ms_per_step_eager_overlap` / `value_eager` with the library's side-stream
+             transposes on), and the same step replayed as a CUDA graph with the two independent directions of each
+             layer on two streams; `value` is the fastest (`execution`)
   e2e        pairs/s through the same module API with the inputs in pinned HOST memory: H2D of every input
              and D2H of the match list inside the timed region (copy stream overlapped with compute)
   roofline   the dominant kernel: algorithmic bytes per launch / its mean device time, CUDA events recorded by
@@ -314,7 +316,12 @@ def run_ours(args):
     F.profile_enable(False)
     launches = (F.launch_count() - l0) // args.steps
     prof = F.profile_collect()
-    F.set_overlap(True)                                 # the library default: finer-level transposes under the coarsest QTAtt level
+    # the same eager step without the per-kernel event pairs (they serialise the launches and defeat the programmatic dependent
+    # launch): once with the side-stream overlap off, once with it on (the library default)
+    for _ in range(3):
+        step()
+    ms_eager_plain = timed(step, args.steps)
+    F.set_overlap(True)
     for _ in range(3):
         step()
     ms_eager_overlap = timed(step, args.steps)
@@ -323,7 +330,8 @@ def run_ours(args):
     # ---- primary pass: the same step replayed as a CUDA graph, the two directions of every layer (independent in the
     # reference model, transformer.py:300) forked onto two streams; the graph ends at the path's one host sync (the match
     # count), the fine stage and the multi-GPU all-gather follow eagerly.  Same kernels, same results.
-    graph_info, ms_step, mode = None, ms_eager, 'eager (one stream)'
+    ms_eager_best = min(ms_eager_plain, ms_eager_overlap)
+    graph_info, ms_step, mode = None, ms_eager_best, 'eager (one stream)'
     if not args.no_graph:
         try:
             gr = pipeline.GraphRunner(hp, dev_in, two_streams=True, whole_step=True)
@@ -337,7 +345,7 @@ def run_ours(args):
             assert int(gout['mconf'].shape[0]) == n_matches, 'graph replay changed the match list'
             ms_graph = timed(gstep, args.steps)
             graph_info = {'ms_per_step': ms_graph, 'matches': n_matches}
-            if ms_graph < ms_eager:
+            if ms_graph < ms_eager_best:
                 ms_step, mode = ms_graph, 'CUDA graph replay of the whole step (no host sync inside), layer directions on two streams'
             del gr
         except Exception as e:      # noqa: BLE001  (capture not possible: the eager number stands)
@@ -575,7 +583,8 @@ def run_ours(args):
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config_dict(wl, n_gpus), 'e2e': e2e, 'gpu_launches': int(launches) * args.steps,
         'gpu_launches_per_step': int(launches), 'clocks': clocks, 'roofline': roofline, 'qtatt_call_roofline': qtatt_call,
-        'execution': mode, 'ms_per_step_eager_instrumented': ms_eager, 'ms_per_step_eager_overlap': ms_eager_overlap, 'value_eager_instrumented': wl.B * n_gpus / (ms_eager / 1000.0),
+        'execution': mode, 'ms_per_step_eager_instrumented': ms_eager, 'ms_per_step_eager': ms_eager_plain, 'ms_per_step_eager_overlap': ms_eager_overlap, 'value_eager_instrumented': wl.B * n_gpus / (ms_eager / 1000.0),
+        'value_eager': wl.B * n_gpus / (ms_eager_overlap / 1000.0),
         'cuda_graph': graph_info, 'numa_binding': numa, 'next_rows': next_rows, 'kernel_ms_per_step': round(kernel_ms / args.steps, 4), 'host_enqueue_ms_attention_calls': round(host_ms, 3), 'breakdown': breakdown, 'matches_per_step': n_matches,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -594,7 +603,7 @@ def run_ours(args):
                 v, spent, detail = cpu_reference_sample(wl, dev_in, os.cpu_count() or 1, sync=torch.cuda.synchronize, ref_kernels=True)
                 line['gpu_reference_kernels_baseline'] = {
                     'value': v, 'unit': UNIT, 'seconds_per_call': detail,
-                    'speedup_eager_vs_eager': round(line['value_eager_instrumented'] / v, 1),
+                    'speedup_eager_vs_eager': round(line['value_eager'] / v, 1),
                     'what': "the reference's GPU path on this B200: its QTAttB / CascadeQTAttB / ScoreComputation data flow (oracle/ref_path.py) "
                             'calling its own three CUDA extensions built unmodified for sm_100a (oracle/_ref), eager, one call of each kind '
                             'scaled by the call counts; matching post-processing and fine matching as plain torch CUDA ops'}

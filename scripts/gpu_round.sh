@@ -24,8 +24,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tra
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'transpose_vec|cascade_att_tile|quad_attention_list' -s 12 -c 3 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_match|extract_|fine_match' -c 6 -f -o $OUT/${TAG}_match $BENCH > $OUT/${TAG}_ncu_c.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'coarse_rowstats|pool2_tokens|fine_window_gather|tf32_residual' -c 4 -f -o $OUT/${TAG}_widen $BENCH > $OUT/${TAG}_ncu_d.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'relative_pe_kernel|score5d_bwd_kernel|value_agg_bwd_kernel|score3d_bwd_kernel' -c 4 -f -o $OUT/${TAG}_widen2 $BENCH > $OUT/${TAG}_ncu_e.log 2>&1
-for r in qtatt cascade match widen widen2; do
+for k in relative_pe_kernel score5d_bwd_kernel value_agg_bwd_kernel score3d_bwd_kernel; do       # one launch of each (they are timed in loops)
+  timeout 600 ncu --set full --clock-control none --import-source on -k $k -c 1 -f -o $OUT/${TAG}_w2_$k $BENCH > $OUT/${TAG}_ncu_e_$k.log 2>&1
+done
+for r in qtatt cascade match widen w2_relative_pe_kernel w2_score5d_bwd_kernel w2_value_agg_bwd_kernel w2_score3d_bwd_kernel; do
   ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null
 done
 ls -la $OUT; du -sh $OUT

@@ -49,7 +49,8 @@ def rows_of(path):
     return out
 
 
-raws = [os.path.join(OUT, f'{TAG}_{r}_raw.csv') for r in ('qtatt', 'cascade', 'match', 'widen', 'widen2')]
+raws = [os.path.join(OUT, f'{TAG}_{r}_raw.csv') for r in ('qtatt', 'cascade', 'match', 'widen', 'w2_relative_pe_kernel', 'w2_score5d_bwd_kernel', 'w2_value_agg_bwd_kernel',
+                                                             'w2_score3d_bwd_kernel')]
 raws = [p for p in raws if os.path.exists(p)]
 buf = io.StringIO()
 buf.write(f'# {TAG} -- B200, `ncu --set full --clock-control none --import-source on`, one launch per kernel\n'
