@@ -106,3 +106,35 @@ def test_fused_relative_pe_full_size(dev, B, nh, hw8_0, hw8_1, s):
     # oracle on the first batch element only (seconds)
     ref, _ = oqt.cascade_qtatt_b(q[:1], k[:1], v[:1], pos[:1].cpu(), rp[:1].cpu(), nh, 1)
     assert (got[:1].cpu() - ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('window', [1, 3])
+def test_fused_relative_pe_other_windows(dev, window):
+    """Windows other than 5x5 take the generic gather kernel (runtime candidate count): tensor path == fused path, both == oracle."""
+    g = torch.Generator().manual_seed(40 + window)
+    B, nh, (h, w), (ho, wo), s, LB = 2, 2, (8, 10), (9, 7), 2, 10
+    H, W, H1, W1 = h * s, w * s, ho * s, wo * s
+    t8 = torch.randint(0, ho * wo, (B, h * w), generator=g)
+    wt, ht = torch.randn(2 * LB + 2, nh, generator=g), torch.randn(2 * LB + 2, nh, generator=g)
+    q, k, v = torch.randn(B, nh * 32, H, W, generator=g), torch.randn(B, nh * 32, H1, W1, generator=g), torch.randn(B, nh * 32, H1, W1, generator=g)
+    pe = F.RelativePE(wt.to(dev), ht.to(dev), LB, t8.to(dev), (h, w), wo)
+    pos = F.window_warp_idx(t8.to(dev), H1 // 2, W1 // 2, window)
+    rp = F.relative_pe(pe, pos, (H, W))
+    assert torch.equal(rp.cpu(), widen.relative_pe(pos.cpu(), t8, wt, ht, LB, (h, w), wo, H))
+    want, up_w = F.cascade_qtatt_forward(q.to(dev), k.to(dev), v.to(dev), pos, rp, nh)
+    for entry in (pos, t8.to(dev)):
+        got, up = F.cascade_qtatt_forward(q.to(dev), k.to(dev), v.to(dev), entry, pe, nh, window=window)
+        assert torch.equal(got, want) and torch.equal(up, up_w)
+    ref, _ = oqt.cascade_qtatt_b(q, k, v, pos.cpu(), rp.cpu(), nh, 1)
+    assert (got.cpu() - ref).abs().max() < 1e-3
+
+
+def test_relative_pe_rejects_mismatched_grids(dev):
+    g = torch.Generator().manual_seed(3)
+    pe = F.RelativePE(torch.randn(22, 2).to(dev), torch.randn(22, 2).to(dev), 10, torch.zeros(1, 48, dtype=torch.int64, device=dev), (6, 8), 9)
+    pos = torch.zeros(1, 48, 25, 2, dtype=torch.int64, device=dev)
+    with pytest.raises(RuntimeError):                       # 12 x 18 is not a multiple of the 6 x 8 grid
+        F.relative_pe(pe, torch.zeros(1, 54, 25, 2, dtype=torch.int64, device=dev), (12, 18))
+    with pytest.raises(RuntimeError):                       # three heads, two-head tables
+        F.cascade_qtatt_forward(torch.zeros(1, 96, 12, 16, device=dev), torch.zeros(1, 96, 14, 18, device=dev), torch.zeros(1, 96, 14, 18, device=dev),
+                                pos, pe, 3)
