@@ -222,7 +222,7 @@ __device__ __forceinline__ void rows_softmax_topk(float *const (&srow)[RP], cons
     __syncwarp();
 }
 
-template <int ROWS>
+template <int ROWS, int NVF>       // NVF: values per lane of the register soft-max / top-k path, sized to the padded row (Sk <= 32 * NVF)
 __global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kernel(CoarseParams p, int s_ld) {
     pdl_sync();
     constexpr int HALVES = 32 / ROWS;              // lane groups sharing a row set (1 for 32 rows, 2 for 16, 4 for 8)
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kern
     constexpr int RPW = (ROWS + NW - 1) / NW;        // rows per warp
     float *mylv = lval + warp * 2 * LIST_CAP;        // two survivor lists per warp (the fast path handles 2 rows at once)
     int *mylp = lpos + warp * 2 * LIST_CAP;
-    constexpr int RP = RPW < 2 ? 1 : 2;              // rows processed together by the register fast path
-    constexpr int NVF = 24;                          // fast path: Sk <= 768 (24 values per lane)
+    constexpr int RP = (RPW < 2 || NVF > 24) ? 1 : 2;   // rows processed together by the register fast path (one when a row alone fills the registers)
+    // register fast path, sized to the padded row: NVF values per lane; 832^2 -> 676 keys -> 22, 640x480 -> 300 -> 16
     if (s_pad <= 32 * NVF) {
         for (int j0 = 0; j0 < RPW; j0 += RP) {
             float *srow[RP], *lvp[RP];
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kern
                 }
             }
         }
-    } else
+    }
+    else
     for (int r = warp; r < ROWS; r += NW) {
         if (row0 + r >= p.Sq) continue;            // warp-uniform
         float *srow = Ss + r * s_ld;
@@ -499,22 +500,29 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED,
                    "coarsest level has %d keys; the dense level supports at most ~6000 (shared memory)", p.Sk);
     CASMTR_REQUIRE(p.topk >= 1 && p.topk <= 32 && p.topk <= p.Sk, CASMTR_E_INVALID, "coarse top-k %d must be in [1, min(32, %d)]", p.topk, p.Sk);
+    // kernel variant: rows per CTA x values per lane of the register soft-max / top-k path (1024^2 -> 1024 keys -> 32, 1152^2 -> 1296 -> 42;
+    // beyond 1344 keys the looped path inside the <.., 42> variant)
+    using Kern = void (*)(CoarseParams, int);
+    static const Kern table[3][6] = {
+        {qtatt_coarse_kernel<32, 8>, qtatt_coarse_kernel<32, 16>, qtatt_coarse_kernel<32, 22>, qtatt_coarse_kernel<32, 24>, qtatt_coarse_kernel<32, 32>, qtatt_coarse_kernel<32, 42>},
+        {qtatt_coarse_kernel<16, 8>, qtatt_coarse_kernel<16, 16>, qtatt_coarse_kernel<16, 22>, qtatt_coarse_kernel<16, 24>, qtatt_coarse_kernel<16, 32>, qtatt_coarse_kernel<16, 42>},
+        {qtatt_coarse_kernel<8, 8>, qtatt_coarse_kernel<8, 16>, qtatt_coarse_kernel<8, 22>, qtatt_coarse_kernel<8, 24>, qtatt_coarse_kernel<8, 32>, qtatt_coarse_kernel<8, 42>}};
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 6; ++j) {
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
         attr_set = true;
     }
+    const int s_pad = (p.Sk + TILE - 1) / TILE * TILE;
+    const int nv = s_pad <= 32 * 8 ? 0 : (s_pad <= 32 * 16 ? 1 : (s_pad <= 32 * 22 ? 2 : (s_pad <= 32 * 24 ? 3 : (s_pad <= 32 * 32 ? 4 : 5))));   // 5: <= 1344 keys, else looped
     dim3 grid((p.Sq + rows - 1) / rows, p.B * p.nh);
     LaunchScope ls(CASMTR_K_QT_COARSE, stream);
-    if (rows == 32) launch_k(qtatt_coarse_kernel<32>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
-    else if (rows == 16) launch_k(qtatt_coarse_kernel<16>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
-    else launch_k(qtatt_coarse_kernel<8>, grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
+    launch_k(table[rows == 32 ? 0 : (rows == 16 ? 1 : 2)][nv], grid, NW * 32, smem, stream, p, coarse_s_ld(p.Sk));
     CASMTR_CHECK_LAUNCH("qtatt_coarse_kernel");
     return CASMTR_OK;
 }

@@ -80,7 +80,9 @@ def test_cfg4_indoor_stage(dev):
     assert (st['conf_matrix'].cpu() - ref['conf01']).abs().max() < 1e-5 and len(want['b_ids']) > 1000
 
 
-@pytest.mark.parametrize('grid,topks', [(64, [32, 16, 8]), (128, [32, 16, 8]), (144, [32, 16, 8]), (80, [32, 16, 16])])
+# coarsest-level keys: 64 -> 256 (8 values per lane), 80 -> 300 (16), 128 -> 1024 (32, one row at a time), 144 -> 1296 (42),
+# 152 -> 1444 (beyond the register path: looped soft-max / top-k)
+@pytest.mark.parametrize('grid,topks', [(64, [32, 16, 8]), (128, [32, 16, 8]), (144, [32, 16, 8]), (152, [32, 16, 8]), (80, [32, 16, 16])])
 def test_cfg5_size_sweep_qtatt(dev, grid, topks):
     nh = 8
     h, w = (60, 80) if grid == 80 else (grid, grid)
