@@ -26,6 +26,8 @@
 //            with shuffles; rank < k owns output slot `rank` (descending order, ties: lower candidate).
 //   A.V      lane = (child slot g, 16-byte chunk dq): 3 LDS.128 per 8 FFMA2, then a transposing
 //            butterfly over g leaves query g's output chunk in the lane; merged and stored raster.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -421,8 +423,14 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
 // counting), survivors {score >= T} (n >= k, typically n - k < 8) are trimmed by removing the minimum n - k times, and
 // the k remaining candidates are emitted in candidate order (the reference's torch.topk order is by score; only the SET
 // is consumed downstream, and every comparison in tests/ is on sets).
-template <int KP, int R, bool TYPE_A, bool DO_TOPK>
-__global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
+// SV ("stream V"): V is not staged.  After the soft-max every warp publishes its sibling's weights as column f of A4[KC][4];
+// warp f then takes the parent candidates f, f+4, .. of ALL four siblings: its lanes = (child slot g, chunk dq) load each V row
+// chunk once, straight from L2 into registers, and feed 8 FFMA2 from one LDS.128 of weights; the per-warp partial sums are
+// transposed over g with a butterfly and added across the warps through a 2 KB buffer aliased onto the (dead) K slab.  Shared
+// memory per item drops from 35 KB to 19 KB (kp = 32): 9 resident items (register-limited) instead of 6, and the A.V loop issues
+// 8 LDS.128 per warp instead of 64 LDS.
+template <int KP, int R, bool TYPE_A, bool DO_TOPK, bool SV>
+__global__ void __launch_bounds__(128, SV ? 9 : 1) quad_cta_kernel(FineParams p) {
     pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;       // warp = sibling f
@@ -437,9 +445,9 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
     const float scale = rsqrtf((float)D);
 
     float *Ks = smem;                                          // [max(KC,32)][32], chunk-swizzled
-    float *Vs = Ks + (KC < 32 ? 32 : KC) * D;                  // [KC][32]
-    float *Qs = Vs + KC * D;                                   // [4][32]
-    float *As = Qs + 4 * D;                                    // [4][KC] attention weights, one row per sibling
+    float *Vs = Ks + (KC < 32 ? 32 : KC) * D;                  // [KC][32]                         (not SV)
+    float *Qs = SV ? Vs : Vs + KC * D;                         // [4][32]
+    float *As = Qs + 4 * D;                                    // [4][KC] attention weights, one row per sibling; SV: A4 [KC][4]
 
     const int off_g = (g >> 1) * p.w1 + (g & 1);
     const int qtok = (2 * py + (f >> 1)) * p.w0 + 2 * px + (f & 1);     // this warp's query token
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
             if (u < kp) {
                 const size_t off = (size_t)tok * C;
                 cp_async16(((u & 1) ? kd1 : kd0) + u * 4 * D, kb + off);
-                cp_async16(vd + u * 4 * D, vb + off);
+                if (!SV) cp_async16(vd + u * 4 * D, vb + off);
             }
         }
         cp_async_commit();
@@ -586,6 +594,75 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
         }
     }
 
+    if (SV) {
+        // ---- A.V, V streamed: warp f = parent candidates f, f+4, .. for all four siblings
+        constexpr int NU = KP ? (KP + 3) / 4 : 8;
+        const float *vb = p.v + (size_t)b * L1 * C + h * D + 4 * dq;
+        float4 vv[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {                         // issued before the barrier: the L2 latency hides behind it
+            const int u = 4 * i + f;
+            const int tok = __shfl_sync(FULL_MASK, base, u & 31) + off_g;
+            vv[i] = u < kp ? ldg4(vb + (size_t)tok * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (32 * r + lane < KC) As[(32 * r + lane) * 4 + f] = a[r];
+        __syncthreads();                                       // A4 complete; every warp is done with the K slab and Q
+        float2 o[4][2];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) o[s4][0] = o[s4][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const int u = 4 * i + f;
+            if (u < kp) {
+                const float4 aw = *reinterpret_cast<const float4 *>(As + (4 * u + g) * 4);
+                const float2 vlo = make_float2(vv[i].x, vv[i].y), vhi = make_float2(vv[i].z, vv[i].w);
+                o[0][0] = __ffma2_rn(make_float2(aw.x, aw.x), vlo, o[0][0]); o[0][1] = __ffma2_rn(make_float2(aw.x, aw.x), vhi, o[0][1]);
+                o[1][0] = __ffma2_rn(make_float2(aw.y, aw.y), vlo, o[1][0]); o[1][1] = __ffma2_rn(make_float2(aw.y, aw.y), vhi, o[1][1]);
+                o[2][0] = __ffma2_rn(make_float2(aw.z, aw.z), vlo, o[2][0]); o[2][1] = __ffma2_rn(make_float2(aw.z, aw.z), vhi, o[2][1]);
+                o[3][0] = __ffma2_rn(make_float2(aw.w, aw.w), vlo, o[3][0]); o[3][1] = __ffma2_rn(make_float2(aw.w, aw.w), vhi, o[3][1]);
+            }
+        }
+        // reduce over g (lane bits 3,4), transposing: the lane ends with sibling g's chunk dq (this warp's candidates only)
+        float ov[4][4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) { ov[s4][0] = o[s4][0].x; ov[s4][1] = o[s4][0].y; ov[s4][2] = o[s4][1].x; ov[s4][3] = o[s4][1].y; }
+        float r2[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float recv = __shfl_xor_sync(FULL_MASK, (g & 2) ? ov[i][c] : ov[i + 2][c], 16);
+                r2[i][c] = ((g & 2) ? ov[i + 2][c] : ov[i][c]) + recv;
+            }
+        float4 m4;
+        {
+            float t[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float recv = __shfl_xor_sync(FULL_MASK, (g & 1) ? r2[0][c] : r2[1][c], 8);
+                t[c] = ((g & 1) ? r2[1][c] : r2[0][c]) + recv;
+            }
+            m4 = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        float *red = Ks;                                       // [4 warps][4 siblings][32], the K slab is dead
+        *reinterpret_cast<float4 *>(red + (f * 4 + g) * D + 4 * dq) = m4;
+        __syncthreads();
+        if (g == 0) {                                          // warp f finishes sibling f: sum of the four warps' partials, in warp order
+            float4 res = *reinterpret_cast<const float4 *>(red + (0 * 4 + f) * D + 4 * dq);
+#pragma unroll
+            for (int w = 1; w < 4; ++w) {
+                const float4 t = *reinterpret_cast<const float4 *>(red + (w * 4 + f) * D + 4 * dq);
+                res.x += t.x; res.y += t.y; res.z += t.z; res.w += t.w;
+            }
+            const float wl = p.wsm ? __ldg(p.wsm + p.level) : 1.f;
+            res.x *= wl; res.y *= wl; res.z *= wl; res.w *= wl;
+            res.x += ap.x; res.y += ap.y; res.z += ap.z; res.w += ap.w;
+            *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + qtok) * C + h * D + 4 * dq) = res;
+        }
+        return;
+    }
     // ---- A.V for sibling f: lane = (child slot g, chunk dq)
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -620,14 +697,15 @@ __global__ void __launch_bounds__(128) quad_cta_kernel(FineParams p) {
 }
 
 __host__ __device__ inline int cta_slab_floats(int kp) { return staged_slab_floats(kp) + 16 * kp; }
+__host__ __device__ inline int cta_sv_slab_floats(int kp) { return warp_slab_floats(kp) + 16 * kp; }     // K + Q + A4
 
-template <int KP, int R, bool TYPE_A, bool DO_TOPK>
+template <int KP, int R, bool TYPE_A, bool DO_TOPK, bool SV>
 int launch_cta_t(const FineParams &p, cudaStream_t stream) {
     const long long items = (long long)(p.h0 / 2) * (p.w0 / 2) * p.nh;       // per batch element
     if (items == 0 || p.B == 0) return CASMTR_OK;
     CASMTR_REQUIRE(items <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
-    const size_t smem = sizeof(float) * cta_slab_floats(p.kp);
-    auto kern = quad_cta_kernel<KP, R, TYPE_A, DO_TOPK>;
+    const size_t smem = sizeof(float) * (SV ? cta_sv_slab_floats(p.kp) : cta_slab_floats(p.kp));
+    auto kern = quad_cta_kernel<KP, R, TYPE_A, DO_TOPK, SV>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -723,8 +801,11 @@ int launch_by_flags(const FineParams &p, cudaStream_t stream) {
     // Last level (4x the items, no top-k): warp per item -- the CTA variant re-reads the K slab once per sibling warp and
     // becomes shared-memory-pipe bound there (ncu: l1tex 85 %), measured 69 us vs 64 us at 832^2.
     const bool topk = p.topk_idx != nullptr;
-    if (p.type_a) return topk ? launch_cta_t<KP, R, true, true>(p, stream) : launch_t<KP, R, false, true, false>(p, stream);
-    return topk ? launch_cta_t<KP, R, false, true>(p, stream) : launch_t<KP, R, false, false, false>(p, stream);
+    static const bool sv = [] { const char *e = getenv("CASMTR_MID_STREAMV"); return !(e && e[0] == '0'); }();
+    if (p.type_a) return topk ? (sv ? launch_cta_t<KP, R, true, true, true>(p, stream) : launch_cta_t<KP, R, true, true, false>(p, stream))
+                              : launch_t<KP, R, false, true, false>(p, stream);
+    return topk ? (sv ? launch_cta_t<KP, R, false, true, true>(p, stream) : launch_cta_t<KP, R, false, true, false>(p, stream))
+                : launch_t<KP, R, false, false, false>(p, stream);
 }
 
 }  // namespace
