@@ -47,6 +47,14 @@ int casmtr_set_pdl(int on) {
     return prev;
 }
 
+static std::atomic<int> g_concurrency{1};
+int casmtr_concurrency() { return g_concurrency.load(std::memory_order_relaxed); }
+int casmtr_set_concurrency(int n) {
+    const int prev = casmtr_concurrency();
+    g_concurrency.store(n < 1 ? 1 : (n > 64 ? 64 : n), std::memory_order_relaxed);
+    return prev;
+}
+
 // ---- fork / join onto a library-owned side stream (casmtr_set_overlap).  A fused call whose first kernel needs only part of
 // the re-laid inputs forks the rest of the layout work onto a side stream and joins it back before the first consumer, so the
 // HBM-bound transposes run under the issue-bound first kernel.  Everything stays ordered with respect to the caller's stream:

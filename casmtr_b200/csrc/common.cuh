@@ -46,6 +46,7 @@ struct LaunchScope {
 // predecessor's tail, the data dependency stays a full one.  launch_k() sets the matching launch attribute
 // (CASMTR_PDL=0 in the environment turns it off; without the attribute both instructions are no-ops).
 bool casmtr_pdl_enabled();
+int casmtr_concurrency();       // casmtr_set_concurrency: how many independent calls the caller keeps in flight (>= 1)
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
     cudaLaunchConfig_t cfg = {};

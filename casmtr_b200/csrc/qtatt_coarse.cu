@@ -28,6 +28,8 @@
 //            tcgen05 needs M >= 64 rows per CTA, i.e. 88 CTAs for 148 SMs while the soft-max / top-k part needs every SM.
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -492,9 +494,11 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
     // 32-row CTAs are the efficient shape (every lane owns a row).  With too few of them to give every SM two, halve the
     // rows per CTA (lane groups split the tokens).  Measured at 832^2, B = 1 (676 rows x 8 heads): 32 rows 76 us, 16 rows
     // 58 us, 8 rows 64 us (every CTA streams all K and V tiles, so below 16 rows the tile traffic and barriers dominate).
-    const long long col = (long long)p.B * p.nh;
+    const long long col = (long long)p.B * p.nh * casmtr_concurrency();      // CTA columns in flight, counting the caller's concurrent calls
     int rows = 32;
     while (rows > 16 && ((p.Sq + rows - 1) / rows) * col < 2 * 148) rows >>= 1;
+    static const int rows_env = [] { const char *e = getenv("CASMTR_COARSE_ROWS"); return e ? atoi(e) : 0; }();
+    if (rows_env == 8 || rows_env == 16 || rows_env == 32) rows = rows_env;
     while (rows > 8 && smem_bytes(p.Sk, rows) > 227 * 1024) rows >>= 1;
     const size_t smem = smem_bytes(p.Sk, rows);
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED,

@@ -57,6 +57,12 @@ def set_overlap(on):
     return bool(lib().casmtr_set_overlap(1 if on else 0))
 
 
+def set_concurrency(n):
+    """How many independent calls the caller keeps in flight (streams / graph branches): a launch-geometry hint
+    (casmtr_set_concurrency); returns the previous value."""
+    return int(lib().casmtr_set_concurrency(int(n)))
+
+
 def profile_collect():
     """-> {kind_name: (device_ms, launches)} accumulated since the last collect (synchronises)."""
     ms = (C.c_double * _lib.K_COUNT)()

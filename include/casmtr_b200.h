@@ -184,6 +184,13 @@ CASMTR_API int casmtr_set_pdl(int on);
  * device) if they do not exist yet -- do that outside a capture.  Returns the previous setting. */
 CASMTR_API int casmtr_set_overlap(int on);
 
+/* Launch-geometry hint: the number of independent calls the caller keeps in flight at once (default 1; e.g. 2 when the two
+ * directions of a layer run on two streams or in two branches of a CUDA graph).  Kernels that trade per-CTA efficiency against
+ * the number of CTAs (the dense coarsest quadtree level: 32-row CTAs stream the K / V tiles half as often as 16-row CTAs but a
+ * single call has too few of them to fill 148 SMs) size their grids for the combined work.  Results do not depend on it.
+ * Returns the previous value. */
+CASMTR_API int casmtr_set_concurrency(int n);
+
 /* ---------------------------------------------------------------- fused cascade window attention (R5) */
 
 CASMTR_API size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1);
