@@ -12,6 +12,8 @@ backbone, F.unfold of the fine map) is out of scope, so the call
 synthetic feature maps of the right shapes (casmtr_b200/synth.py).  bench.py, the full-size GPU
 tests and smoke() all drive the path through this one class, via the public module API.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -228,7 +230,7 @@ class GraphRunner:
             prev = F.set_pdl(not two_streams)
             # same reasoning for the library's own side-stream overlap of the transposes (casmtr_set_overlap): with the other
             # direction already co-running it only adds contention (measured: 2.186 ms with, 2.178 ms without; eager single
-            # stream: 3.14 ms with, 3.18 ms without)
+            # stream: 3.14 ms with, 3.18 ms without; re-checked with the r02 kernels: 2.066 ms with, 2.058 ms without)
             prev_ov = F.set_overlap(not two_streams)
             # launch geometry is fixed at capture: tell the library that two calls run side by side (the dense coarsest level
             # then keeps its 32-row CTAs: 2.083 -> 2.066 ms per step)
