@@ -109,3 +109,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libcasmtr_b200.so')
     with pytest.raises(ImportError, match='no CPU fallback'):
         _lib.lib()
+
+
+def test_host_mirror_of_the_relative_pe_module_needs_no_gpu():
+    """CascadeRelativePE carries the reference's parameter names and LB rule (transformer.py:356-362); constructing it and loading a
+    state dict is pure host logic."""
+    import torch
+    from casmtr_b200.modules.attention_layers import CascadeRelativePE
+    m = CascadeRelativePE(4, window_size=5, sr_ratio=2)
+    assert m.LB == 10 and m.h_pos_bias.weight.shape == (22, 4) and m.w_pos_bias.weight.shape == (22, 4)
+    assert CascadeRelativePE(2, 5, 4).LB == 30 and CascadeRelativePE(2, 5, 4).w_pos_bias.weight.shape == (64, 2)
+    m.load_state_dict({'h_pos_bias.weight': torch.zeros(22, 4), 'w_pos_bias.weight': torch.ones(22, 4)})
+    with pytest.raises(RuntimeError):                    # CPU tensors are refused, nothing falls back
+        m.get_relative_pe({'hw0_8c': (6, 8), 'hw1_8c': (6, 8), 'stage_8c': {'next_idx_c01': torch.zeros(1, 48, dtype=torch.long)}},
+                          12, torch.zeros(1, 48, 25, 2, dtype=torch.long), None, 0)
+
+
+def test_tuning_switches_round_trip():
+    from casmtr_b200 import _lib
+    lib = _lib.lib()
+    prev = lib.casmtr_set_concurrency(2)
+    assert lib.casmtr_set_concurrency(prev) == 2 and lib.casmtr_set_concurrency(0) == prev and lib.casmtr_set_concurrency(prev) == 1
