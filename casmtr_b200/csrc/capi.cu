@@ -63,7 +63,10 @@ int casmtr_set_concurrency(int n) {
 // outside any capture where possible (casmtr_set_overlap(1) or the first eager call), and handed out round-robin.
 namespace {
 struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
-constexpr int SIDE_LANES = 8, SIDE_MAX_DEV = 16;
+// Two lanes per device: enough for the two directions of a layer, and few enough that caller stream + lanes + a copy stream + NCCL's
+// stream stay within the 8 hardware work queues of a default CUDA context (streams that share a queue pick up false dependencies:
+// a lane queued behind an NCCL kernel that waits for a peer rank stalls the call that joins it).
+constexpr int SIDE_LANES = 2, SIDE_MAX_DEV = 16;
 std::mutex g_side_mu;
 SideLane g_side[SIDE_MAX_DEV][SIDE_LANES];
 bool g_side_ready[SIDE_MAX_DEV];

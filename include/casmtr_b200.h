@@ -180,7 +180,7 @@ CASMTR_API int casmtr_set_pdl(int on);
  * call forks the NCHW -> token-major transposes of all but the coarsest pyramid level onto a library-owned side stream and
  * joins them back before the first fine level, so they run under the coarsest level's kernel.  The call stays fully ordered
  * with respect to the caller's stream (event fork after the caller's prior work, event join before the call's later kernels
- * and anything the caller enqueues afterwards) and can be stream-captured.  Turning it on creates the side streams (8 per
+ * and anything the caller enqueues afterwards) and can be stream-captured.  Turning it on creates the side streams (2 per
  * device) if they do not exist yet -- do that outside a capture.  Returns the previous setting. */
 CASMTR_API int casmtr_set_overlap(int on);
 
