@@ -130,3 +130,32 @@ def test_tuning_switches_round_trip():
     lib = _lib.lib()
     prev = lib.casmtr_set_concurrency(2)
     assert lib.casmtr_set_concurrency(prev) == 2 and lib.casmtr_set_concurrency(0) == prev and lib.casmtr_set_concurrency(prev) == 1
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/casmtr_b200.h is the contract a non-Python host binds: it must compile as strict C99 and a C program must link
+    against the library with nothing but -lcasmtr_b200 (no torch, no C++ runtime symbols leaking into the interface)."""
+    import shutil
+    import subprocess
+    from casmtr_b200 import build
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    lib = build.build()
+    src = tmp_path / 't.c'
+    src.write_text('#include "casmtr_b200.h"\n'
+                   'int main(void) {\n'
+                   '    casmtr_relpe_desc pe; casmtr_qtatt_desc qd; casmtr_extract_desc ed;\n'
+                   '    (void)pe; (void)qd; (void)ed;\n'
+                   '    if (casmtr_version() != CASMTR_VERSION) return 1;\n'
+                   '    /* argument validation needs no device: a null descriptor is refused with a message */\n'
+                   '    if (casmtr_qtatt_workspace_bytes((const casmtr_qtatt_desc *)0) != 0) return 2;\n'
+                   '    return casmtr_last_error_string()[0] ? 0 : 3;\n'
+                   '}\n')
+    exe = tmp_path / 't'
+    inc = os.path.join(ROOT, 'include')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, str(src), '-o', str(exe),
+                        '-L', os.path.dirname(lib), '-lcasmtr_b200', '-Wl,-rpath,' + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
