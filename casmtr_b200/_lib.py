@@ -21,7 +21,10 @@ class QtattDesc(C.Structure):
     _fields_ = [('B', C.c_int), ('nhead', C.c_int), ('D', C.c_int), ('levels', C.c_int), ('type', C.c_int),
                 ('qh', C.c_int * MAX_LEVELS), ('qw', C.c_int * MAX_LEVELS),
                 ('kh', C.c_int * MAX_LEVELS), ('kw', C.c_int * MAX_LEVELS),
-                ('topks', C.c_int * MAX_LEVELS)]
+                ('topks', C.c_int * MAX_LEVELS), ('flags', C.c_int), ('weight_len', C.c_int), ('concurrent_calls', C.c_int)]
+
+
+QT_NO_OVERLAP, QT_SIMT_COARSE = 1, 2        # casmtr_qtatt_desc.flags
 
 
 class ExtractDesc(C.Structure):
@@ -64,7 +67,6 @@ SIGNATURES = {
                                         + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_set_pdl': (C.c_int, [C.c_int]),
     'casmtr_set_overlap': (C.c_int, [C.c_int]),
-    'casmtr_set_concurrency': (C.c_int, [C.c_int]),
     'casmtr_window_idx_fwd': (C.c_int, [c_i64_p, c_i64_p] + [C.c_int] * 5 + [C.c_void_p]),
     'casmtr_cascade_qtatt_window_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, C.c_int, c_float_p, c_float_p, c_i64_p]
                                         + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p]),

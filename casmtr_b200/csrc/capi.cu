@@ -31,28 +31,41 @@ const char *const g_kind_names[CASMTR_K_COUNT] = {"layout", "qt_coarse", "qt_fin
                                                   "cascade_match", "extract", "fine_match", "ops", "cascade_fallback", "coarse_match"};
 }  // namespace
 
-static std::atomic<int> g_pdl{-1};
+// Launch options are per calling THREAD (thread_local), never process-global: two host threads driving two devices / streams
+// cannot change each other's launch geometry, and what a stream capture bakes in is what the capturing thread asked for.
+static int env_default(const char *name) {
+    const char *e = getenv(name);
+    return (e && e[0] == '0') ? 0 : 1;
+}
+static thread_local int t_pdl = -1;
 bool casmtr_pdl_enabled() {
-    int v = g_pdl.load(std::memory_order_relaxed);
-    if (v < 0) {
-        const char *e = getenv("CASMTR_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
-        g_pdl.store(v, std::memory_order_relaxed);
-    }
-    return v != 0;
+    if (t_pdl < 0) t_pdl = env_default("CASMTR_PDL");
+    return t_pdl != 0;
 }
 int casmtr_set_pdl(int on) {
     const int prev = casmtr_pdl_enabled() ? 1 : 0;
-    g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+    t_pdl = on ? 1 : 0;
     return prev;
 }
 
-static std::atomic<int> g_concurrency{1};
-int casmtr_concurrency() { return g_concurrency.load(std::memory_order_relaxed); }
-int casmtr_set_concurrency(int n) {
-    const int prev = casmtr_concurrency();
-    g_concurrency.store(n < 1 ? 1 : (n > 64 ? 64 : n), std::memory_order_relaxed);
-    return prev;
+// concurrent calls of the running entry point (casmtr_qtatt_desc::concurrent_calls), visible to the launchers below it
+static thread_local int t_concurrency = 1;
+int casmtr_concurrency() { return t_concurrency; }
+struct ConcurrencyScope {
+    int prev;
+    explicit ConcurrencyScope(int n) : prev(t_concurrency) { t_concurrency = n < 1 ? 1 : (n > 64 ? 64 : n); }
+    ~ConcurrencyScope() { t_concurrency = prev; }
+};
+
+int casmtr_sm_count() {
+    static std::atomic<int> cache[64];
+    const int dev = PerDeviceOnce::device();
+    int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 
 // ---- fork / join onto a library-owned side stream (casmtr_set_overlap).  A fused call whose first kernel needs only part of
@@ -67,48 +80,56 @@ struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; };
 // stream stay within the 8 hardware work queues of a default CUDA context (streams that share a queue pick up false dependencies:
 // a lane queued behind an NCCL kernel that waits for a peer rank stalls the call that joins it).
 constexpr int SIDE_LANES = 2, SIDE_MAX_DEV = 16;
-std::mutex g_side_mu;
+std::mutex g_side_mu;                       // creation of the lanes
+std::mutex g_side_use[SIDE_MAX_DEV];        // one caller at a time enqueues fork ... join on a device's lanes (see LaneGuard)
 SideLane g_side[SIDE_MAX_DEV][SIDE_LANES];
 bool g_side_ready[SIDE_MAX_DEV];
 unsigned g_side_next[SIDE_MAX_DEV];
-std::atomic<int> g_overlap{-1};
+thread_local int t_overlap = -1;
 
 bool overlap_enabled() {
-    int v = g_overlap.load(std::memory_order_relaxed);
-    if (v < 0) {
-        const char *e = getenv("CASMTR_OVERLAP");
-        v = (e && e[0] == '0') ? 0 : 1;
-        g_overlap.store(v, std::memory_order_relaxed);
-    }
-    return v != 0;
+    if (t_overlap < 0) t_overlap = env_default("CASMTR_OVERLAP");
+    return t_overlap != 0;
 }
 
-// a lane of the current device, or nullptr (overlap off / lanes unavailable: the caller then stays on its own stream)
-SideLane *side_lane() {
-    if (!overlap_enabled()) return nullptr;
+// A lane of the current device, or nullptr (overlap off / lanes unavailable: the caller then stays on its own stream).
+// The returned guard owns the device's lane mutex: the fork record + wait and the join record + wait of a call are enqueued
+// without another host thread's record landing between them (a lane has ONE fork and ONE join event; an interleaved record
+// would make this call's wait observe the other caller's stream position).
+struct LaneGuard {
+    SideLane *lane = nullptr;
+    std::unique_lock<std::mutex> lock;
+};
+LaneGuard side_lane(bool want) {
+    LaneGuard g;
+    if (!want || !overlap_enabled()) return g;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SIDE_MAX_DEV) return nullptr;
-    std::lock_guard<std::mutex> lk(g_side_mu);
-    if (!g_side_ready[dev]) {
-        for (int i = 0; i < SIDE_LANES; ++i) {
-            SideLane &l = g_side[dev][i];
-            if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
-                cudaGetLastError();
-                return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SIDE_MAX_DEV) { cudaGetLastError(); return g; }
+    {
+        std::lock_guard<std::mutex> lk(g_side_mu);
+        if (!g_side_ready[dev]) {
+            for (int i = 0; i < SIDE_LANES; ++i) {
+                SideLane &l = g_side[dev][i];
+                if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError();
+                    return g;
+                }
             }
+            g_side_ready[dev] = true;
         }
-        g_side_ready[dev] = true;
     }
-    return &g_side[dev][g_side_next[dev]++ % SIDE_LANES];
+    g.lock = std::unique_lock<std::mutex>(g_side_use[dev]);
+    g.lane = &g_side[dev][g_side_next[dev]++ % SIDE_LANES];
+    return g;
 }
 }  // namespace
 
 int casmtr_set_overlap(int on) {
     const int prev = overlap_enabled() ? 1 : 0;
-    g_overlap.store(on ? 1 : 0, std::memory_order_relaxed);
-    if (on) side_lane();                    // create the lanes now (outside a stream capture)
+    t_overlap = on ? 1 : 0;
+    if (on) side_lane(true);                // create the lanes now (outside a stream capture)
     return prev;
 }
 
@@ -243,6 +264,8 @@ static int check_qtatt_desc(const casmtr_qtatt_desc *d) {
     CASMTR_REQUIRE(d->D == 32, CASMTR_E_UNSUPPORTED, "qtatt: head dim %d unsupported, the fused kernels implement D == 32", d->D);
     CASMTR_REQUIRE(d->B >= 1 && d->nhead >= 1, CASMTR_E_INVALID, "qtatt: B=%d nhead=%d", d->B, d->nhead);
     CASMTR_REQUIRE(d->type == 0 || d->type == 1, CASMTR_E_INVALID, "qtatt: type=%d must be 0 (B) or 1 (A)", d->type);
+    CASMTR_REQUIRE(d->weight_len == 0 || (d->weight_len >= d->levels && d->weight_len <= 64), CASMTR_E_INVALID,
+                   "qtatt: weight_len=%d must be 0 or in [levels=%d, 64]", d->weight_len, d->levels);
     for (int l = 0; l < d->levels; ++l) {
         CASMTR_REQUIRE(d->qh[l] > 0 && d->qw[l] > 0 && d->kh[l] > 0 && d->kw[l] > 0, CASMTR_E_INVALID, "qtatt: empty grid at level %d", l);
         if (l + 1 < d->levels)
@@ -319,7 +342,9 @@ int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
     // The dense coarsest level needs only the coarsest maps (1/16 of the finest): with a side lane the finer levels' maps
     // (95 % of the bytes, HBM-bound) are re-laid under the coarsest level's kernel (issue-bound) and joined before the first
     // fine level.  Without a lane: one batched launch on the caller's stream.
-    SideLane *lane = d->levels >= 2 ? side_lane() : nullptr;
+    LaneGuard guard = side_lane(d->levels >= 2 && !(d->flags & CASMTR_QT_NO_OVERLAP));      // holds the device's lane mutex until the call returns
+    SideLane *lane = guard.lane;
+    ConcurrencyScope cc(d->concurrent_calls);
     if (lane && (cudaEventRecord(lane->fork, stream) != cudaSuccess || cudaStreamWaitEvent(lane->stream, lane->fork, 0) != cudaSuccess)) {
         cudaGetLastError();
         lane = nullptr;
@@ -365,6 +390,7 @@ int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const f
     CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "qtatt_tokens: workspace %zu < %zu bytes", workspace_bytes, ws.off);
     const int C = d->nhead * d->D;
     bf.q[0] = const_cast<float *>(q0); bf.k[0] = const_cast<float *>(k0); bf.v[0] = const_cast<float *>(v0);   // read in place
+    ConcurrencyScope cc(d->concurrent_calls);
     for (int l = 1; l < d->levels; ++l) {
         PoolJobs pj;
         pj.n = 3;
@@ -405,7 +431,7 @@ static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf,
             CoarseParams cp;
             cp.q = bf.q[l]; cp.k = bf.k[l]; cp.v = bf.v[l];
             cp.acc = dst; cp.topk_idx = bf.tk_idx[0]; cp.topk_score = bf.tk_sc[0];
-            cp.level_weight = wts; cp.levels = d->levels; cp.wsm = wts ? bf.wsm : nullptr;
+            cp.level_weight = wts; cp.levels = d->levels; cp.n_weights = d->weight_len > 0 ? d->weight_len : d->levels; cp.wsm = wts ? bf.wsm : nullptr;
             cp.B = d->B; cp.Sq = d->qh[l] * d->qw[l]; cp.Sk = d->kh[l] * d->kw[l];
             cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type;
             rc = launch_qtatt_coarse(cp, stream);

@@ -138,6 +138,7 @@ __device__ __forceinline__ void match_row(const MatchParams &p, const Dir &d, si
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 4));
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 8));
     arg = min(arg, __shfl_xor_sync(FULL_MASK, arg, 16));
+    if (arg == 0x7fffffff) arg = 0;              // NaN scores: nothing compares equal to the max; keep the gather in bounds (the confidence is NaN, as in the reference)
     if (d.conf) {                                // lane (mine, r) stores chunks r, r+4, ..: 32 consecutive k per store
         const int r = lane & 3;
 #pragma unroll
@@ -344,6 +345,7 @@ __device__ __forceinline__ void match_cell(const MatchParams &p, float *slab, si
         }
         sum = warp_sum(sum);
         arg = __reduce_min_sync(FULL_MASK, arg);
+        if (arg == 0x7fffffff) arg = 0;          // NaN scores (see the row kernel)
         const size_t row = ROWQ(f);
         if (d.conf) {
 #pragma unroll
@@ -382,15 +384,16 @@ int launch_cascade_match(const MatchParams &p, cudaStream_t stream) {
         int wpc = (int)((110 * 1024) / per_warp);               // two CTAs per SM
         wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
         const size_t smem = per_warp * wpc;
-        const unsigned blocks = listed ? 2 * 148 : (unsigned)((rows / 4 + wpc - 1) / wpc);
-        static bool attr_set = false;
-        if (!attr_set) {
+        const unsigned blocks = listed ? 2 * (unsigned)casmtr_sm_count() : (unsigned)((rows / 4 + wpc - 1) / wpc);
+        static PerDeviceOnce once;
+        const int dev = PerDeviceOnce::device();
+        if (!once.done(dev)) {
             cudaError_t e = cudaFuncSetAttribute(cascade_match_cell_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_cell_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-            attr_set = true;
+            once.mark(dev);
         }
         if (p.C == 128) launch_k(cascade_match_cell_kernel<32>, blocks, wpc * 32, smem, stream, q, wpc);
         else launch_k(cascade_match_cell_kernel<16>, blocks, wpc * 32, smem, stream, q, wpc);

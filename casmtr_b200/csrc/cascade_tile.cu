@@ -114,7 +114,9 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     const int kk = k0 + k;
                     bad |= ((int)wv[k].x ^ (r0 + kk / 5)) | ((int)wv[k].y ^ (c0 + kk % 5));
                 }
-                regular = bad == 0;
+                // ... that lies inside the key grid: an out-of-grid window reads clamped / row-wrapped tokens in the reference
+                // (torch.clamp of the flat index, quadtree_attention.py:428) but zero-filled rows from an out-of-bounds TMA tile
+                regular = bad == 0 && r0 >= 0 && c0 >= 0 && 2 * (r0 + 5) <= p.h1 && 2 * (c0 + 5) <= p.w1;
             }
             const bool mirror_ok = __shfl_xor_sync(FULL_MASK, regular, 16);
             regular = regular && mirror_ok;
@@ -347,18 +349,18 @@ int launch_cascade_att_tile(const float *q, const float *k, const float *v, cons
     const int hp = h0 / 2, wp = w0 / 2;
     p.tiles_x = (wp + TP - 1) / TP; p.tiles_y = (hp + TP - 1) / TP;
     const size_t smem = cascade_tile_smem_bytes();
-    static int n_sm = 0;
-    if (!n_sm) {
+    static PerDeviceOnce once;
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaSuccess;
         for (auto kern : {cascade_att_tile_kernel<false>, cascade_att_tile_kernel<true>}) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
-        int dev = 0;
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) { n_sm = 0; casmtr_set_error("cascade tile kernel setup: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        if (e != cudaSuccess) { casmtr_set_error("cascade tile kernel setup: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        once.mark(dev);
     }
+    const int n_sm = casmtr_sm_count();
     if (cudaMemsetAsync(fb_count, 0, sizeof(int), stream) != cudaSuccess) { casmtr_set_error("cudaMemsetAsync failed"); return CASMTR_E_CUDA; }
     const long long n_work = (long long)p.tiles_x * p.tiles_y * nh * B;
     CASMTR_REQUIRE(n_work < 0x7fffffffLL, CASMTR_E_UNSUPPORTED, "cascade tile grid too large");

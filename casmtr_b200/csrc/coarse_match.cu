@@ -345,11 +345,12 @@ int launch_coarse_match(const float *feat0, const float *feat1, const uint8_t *m
     }
     if (rc != CASMTR_OK) return rc;
     const size_t smem = 1024 + SM_TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(coarse_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-        attr_set = true;
+        once.mark(dev);
     }
     {
         LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);

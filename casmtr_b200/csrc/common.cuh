@@ -46,7 +46,7 @@ struct LaunchScope {
 // predecessor's tail, the data dependency stays a full one.  launch_k() sets the matching launch attribute
 // (CASMTR_PDL=0 in the environment turns it off; without the attribute both instructions are no-ops).
 bool casmtr_pdl_enabled();
-int casmtr_concurrency();       // casmtr_set_concurrency: how many independent calls the caller keeps in flight (>= 1)
+int casmtr_concurrency();       // casmtr_qtatt_desc::concurrent_calls of the running entry point (>= 1)
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
@@ -63,6 +63,19 @@ __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 #endif
+
+// ---- per-device one-time setup.  cudaFuncSetAttribute applies to the CURRENT device only, so the "already done" flag of a
+// launcher is one bit per device ordinal, not one per process.  Setting an attribute twice is harmless, so two host threads
+// racing through the first call both do the setup and both publish the bit (release / acquire on the atomic).
+#include <atomic>
+struct PerDeviceOnce {
+    std::atomic<uint64_t> bits{0};
+    // device ordinal of the calling thread (0 if it cannot be read; ordinals >= 64 never cache and redo the setup each call)
+    static int device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
+    bool done(int dev) const { return dev >= 0 && dev < 64 && ((bits.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void mark(int dev) { if (dev >= 0 && dev < 64) bits.fetch_or(1ull << dev, std::memory_order_release); }
+};
+int casmtr_sm_count();          // SM count of the current device (cached per device; capi.cu)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

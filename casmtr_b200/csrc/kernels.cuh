@@ -37,7 +37,7 @@ struct CoarseParams {
     float *topk_score;          // [B,Sq,nh,k]
     const float *level_weight;  // raw QTAttB.weight (device) or NULL
     float *wsm;                 // [levels] out: softmax(level_weight), written once for the finer levels' kernels (NULL if no weights)
-    int levels;
+    int levels, n_weights;      // pyramid levels; entries of level_weight the soft-max runs over (>= levels)
     int B, Sq, Sk, nh, topk;
     int type_a;
 };

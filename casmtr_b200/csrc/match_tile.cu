@@ -222,6 +222,7 @@ __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel
             }
             sum = warp_sum(sum);
             arg = __reduce_min_sync(FULL_MASK, arg);
+            if (arg == 0x7fffffff) arg = 0;         // NaN scores: keep next_idx a valid token of the window
             const size_t row = ROWQ(f);
             if (conf) {
 #pragma unroll
@@ -259,15 +260,15 @@ int launch_cascade_match_tile(const MatchParams &p, cudaStream_t stream) {
     if (rc == CASMTR_OK) rc = make_tile_map(&maps.qry[1], p.feat1, p.B, h1, p.w1, p.C, 2 * TP, 2 * TP, false);
     if (rc != CASMTR_OK) return rc;
     const size_t smem = match_tile_smem_bytes();
-    static int n_sm = 0;
-    if (!n_sm) {
+    static PerDeviceOnce once;
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(cascade_match_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(cascade_match_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int dev = 0;
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) { n_sm = 0; casmtr_set_error("cascade match tile kernel setup: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        if (e != cudaSuccess) { casmtr_set_error("cascade match tile kernel setup: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
+        once.mark(dev);
     }
+    const int n_sm = casmtr_sm_count();
     if (cudaMemsetAsync(p.fb_count, 0, sizeof(int), stream) != cudaSuccess) { casmtr_set_error("cudaMemsetAsync failed"); return CASMTR_E_CUDA; }
     const int tiles0 = ((h0 / 2 + TP - 1) / TP) * ((p.w0 / 2 + TP - 1) / TP), tiles1 = ((h1 / 2 + TP - 1) / TP) * ((p.w1 / 2 + TP - 1) / TP);
     const long long n_work = (long long)p.B * (tiles0 + tiles1);

@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(NW * 32, ROWS == 32 ? 2 : 3) qtatt_coarse_kern
     float w0 = 1.f;
     if (p.level_weight) {                           // softmax over the level weights (:264)
         float mx = -INFINITY, den = 0.f;
-        for (int l = 0; l < p.levels; ++l) mx = fmaxf(mx, __ldg(p.level_weight + l));
-        for (int l = 0; l < p.levels; ++l) den += expf(__ldg(p.level_weight + l) - mx);
+        for (int l = 0; l < p.n_weights; ++l) mx = fmaxf(mx, __ldg(p.level_weight + l));
+        for (int l = 0; l < p.n_weights; ++l) den += expf(__ldg(p.level_weight + l) - mx);
         w0 = expf(__ldg(p.level_weight) - mx) / den;
         if (p.wsm && blockIdx.x == 0 && blockIdx.y == 0 && tid < p.levels)      // the finer levels read their weight from here
             p.wsm[tid] = expf(__ldg(p.level_weight + tid) - mx) / den;
@@ -511,8 +511,9 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
         {qtatt_coarse_kernel<32, 8>, qtatt_coarse_kernel<32, 16>, qtatt_coarse_kernel<32, 22>, qtatt_coarse_kernel<32, 24>, qtatt_coarse_kernel<32, 32>, qtatt_coarse_kernel<32, 42>},
         {qtatt_coarse_kernel<16, 8>, qtatt_coarse_kernel<16, 16>, qtatt_coarse_kernel<16, 22>, qtatt_coarse_kernel<16, 24>, qtatt_coarse_kernel<16, 32>, qtatt_coarse_kernel<16, 42>},
         {qtatt_coarse_kernel<8, 8>, qtatt_coarse_kernel<8, 16>, qtatt_coarse_kernel<8, 22>, qtatt_coarse_kernel<8, 24>, qtatt_coarse_kernel<8, 32>, qtatt_coarse_kernel<8, 42>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaSuccess;
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 6; ++j) {
@@ -520,7 +521,7 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             }
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-        attr_set = true;
+        once.mark(dev);
     }
     const int s_pad = (p.Sk + TILE - 1) / TILE * TILE;
     const int nv = s_pad <= 32 * 8 ? 0 : (s_pad <= 32 * 16 ? 1 : (s_pad <= 32 * 22 ? 2 : (s_pad <= 32 * 24 ? 3 : (s_pad <= 32 * 32 ? 4 : 5))));   // 5: <= 1344 keys, else looped

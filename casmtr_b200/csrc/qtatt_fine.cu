@@ -708,12 +708,13 @@ int launch_cta_t(const FineParams &p, cudaStream_t stream) {
     CASMTR_REQUIRE(items <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
     const size_t smem = sizeof(float) * (SV ? cta_sv_slab_floats(p.kp) : cta_slab_floats(p.kp));
     auto kern = quad_cta_kernel<KP, R, TYPE_A, DO_TOPK, SV>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;                                                // one flag per template instance and device
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-        attr_set = true;
+        once.mark(dev);
     }
     LaunchScope ls(DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST, stream);
     launch_k(kern, dim3((unsigned)items, p.B), 128, smem, stream, p);
@@ -765,12 +766,13 @@ int launch_t(const FineParams &p, cudaStream_t stream) {
     const long long blocks = (items + wpc - 1) / wpc;
     CASMTR_REQUIRE(blocks <= 0x7fffffffLL && p.B <= 65535, CASMTR_E_UNSUPPORTED, "quad attention grid too large");
     auto kern = quad_attention_kernel<KP, R, CASCADE, TYPE_A, DO_TOPK, PE>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;                                                // one flag per template instance and device
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-        attr_set = true;
+        once.mark(dev);
     }
     LaunchScope ls(CASCADE ? CASMTR_K_CASCADE_ATT : (DO_TOPK ? CASMTR_K_QT_FINE_MID : CASMTR_K_QT_FINE_LAST), stream);
     launch_k(kern, dim3((unsigned)blocks, p.B), wpc * 32, smem, stream, p, wpc);
@@ -785,12 +787,13 @@ int launch_list_t(const FineParams &p, cudaStream_t stream) {
     wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
     const size_t smem = per_warp * wpc;
     auto kern = quad_attention_list_kernel<KP, R, PE>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;                                                // one flag per template instance and device
+    const int dev = PerDeviceOnce::device();
+    if (!once.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
-        attr_set = true;
+        once.mark(dev);
     }
     LaunchScope ls(CASMTR_K_CASCADE_FALLBACK, stream);
     launch_k(kern, 2 * 148, wpc * 32, smem, stream, p, wpc);             // persistent: the list length is only known on the device

@@ -47,7 +47,8 @@ def profile_enable(on=True):
 
 
 def set_pdl(on):
-    """Programmatic dependent launch of the hot-path kernels on/off (casmtr_set_pdl); returns the previous setting."""
+    """Programmatic dependent launch of the hot-path kernels on/off for the calling thread (casmtr_set_pdl); returns the
+    previous setting."""
     return bool(lib().casmtr_set_pdl(1 if on else 0))
 
 
@@ -55,12 +56,6 @@ def set_overlap(on):
     """Side-stream overlap of the finer levels' transposes with the coarsest level inside casmtr_qtatt_fwd (casmtr_set_overlap);
     returns the previous setting.  Call it once outside any CUDA-graph capture: it creates the library's side streams."""
     return bool(lib().casmtr_set_overlap(1 if on else 0))
-
-
-def set_concurrency(n):
-    """How many independent calls the caller keeps in flight (streams / graph branches): a launch-geometry hint
-    (casmtr_set_concurrency); returns the previous value."""
-    return int(lib().casmtr_set_concurrency(int(n)))
 
 
 def profile_collect():
@@ -168,10 +163,12 @@ def nchw_to_tokens(x):
 
 
 # ------------------------------------------------------------------------------------- fused QuadTree attention
-def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B', return_topk=False):
+def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B', return_topk=False, flags=0, concurrent_calls=0):
     """Fused QTAttA / QTAttB forward.  queries/keys/values: lists finest->coarsest of [B,C,H,W] fp32.
     Returns message [B, L_finest, nhead, D] (and, with return_topk, per-level lists of top-k key
-    indices [B,L,k,nhead] int64 and scores, processing order, last level omitted)."""
+    indices [B,L,k,nhead] int64 and scores, processing order, last level omitted).
+    weight: the whole QTAttB.weight parameter (its soft-max runs over all entries, level i uses entry i).
+    flags: _lib.QT_* bits; concurrent_calls: launch-geometry hint (casmtr_qtatt_desc)."""
     n = len(queries)
     if not (len(keys) == n and len(values) == n and 1 <= n <= _lib.MAX_LEVELS):
         raise RuntimeError(f'need 1..{_lib.MAX_LEVELS} pyramid levels, got {n}')
@@ -184,6 +181,7 @@ def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B
     B, Cc = qs[0].shape[:2]
     d = QtattDesc()
     d.B, d.nhead, d.D, d.levels, d.type = B, nhead, Cc // nhead, n, 1 if attn_type == 'A' else 0
+    d.flags, d.concurrent_calls = int(flags), int(concurrent_calls)
     for l in range(n):
         if ks[l].shape != vs[l].shape or qs[l].shape[:2] != (B, Cc) or ks[l].shape[:2] != (B, Cc):
             raise RuntimeError(f'inconsistent shapes at level {l}')
@@ -196,6 +194,7 @@ def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B
         weight = _chk(weight.detach().to(torch.float32).contiguous(), 'weight', torch.float32)
         if weight.numel() < n:
             raise RuntimeError('weight shorter than the pyramid')
+        d.weight_len = weight.numel()
     L0 = d.qh[0] * d.qw[0]
     out = torch.empty(B, L0, nhead, Cc // nhead, dtype=torch.float32, device=dev)
     arr = C.c_void_p * n
@@ -221,7 +220,7 @@ def qtatt_forward(queries, keys, values, topks, nhead, weight=None, attn_type='B
     return out
 
 
-def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn_type='B', return_topk=False):
+def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn_type='B', return_topk=False, flags=0, concurrent_calls=0):
     """QTAttA / QTAttB from the finest level only, token-major: q0 [B, hq*wq, C], k0 / v0 [B, hk*wk, C] fp32; the
     avg-pool pyramid of len(topks) levels is built inside (casmtr_qtatt_tokens_fwd).  Returns as qtatt_forward."""
     _chk(q0, 'q0', torch.float32), _chk(k0, 'k0', torch.float32), _chk(v0, 'v0', torch.float32)
@@ -237,6 +236,7 @@ def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn
     dev = q0.device
     d = QtattDesc()
     d.B, d.nhead, d.D, d.levels, d.type = B, nhead, Cc // nhead, n, 1 if attn_type == 'A' else 0
+    d.flags, d.concurrent_calls = int(flags), int(concurrent_calls)
     for l in range(n):
         d.qh[l], d.qw[l], d.kh[l], d.kw[l], d.topks[l] = hq >> l, wq >> l, hk >> l, wk >> l, int(topks[l])
     if d.type == 0:
@@ -245,6 +245,7 @@ def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn
         weight = _chk(weight.detach().to(torch.float32).contiguous(), 'weight', torch.float32)
         if weight.numel() < n:
             raise RuntimeError('weight shorter than the pyramid')
+        d.weight_len = weight.numel()
     out = torch.empty(B, Lq, nhead, Cc // nhead, dtype=torch.float32, device=dev)
     arr = C.c_void_p * n
     tk_idx, tk_sc, ia, sa = [], [], None, None

@@ -79,7 +79,7 @@ class QuadtreeAttention(nn.Module):
             raise NotImplementedError('lepe needs the NCHW value pyramid: call QTAttB through its own forward')
         q, k, v = _project(self.q_proj, x), _project(self.k_proj, target), _project(self.v_proj, target)
         topks = list(self.py_att.topks)[:self.scale]
-        weight = self.py_att.weight[:self.scale] if self.attn_type != 'A' else None
+        weight = self.py_att.weight if self.attn_type != 'A' else None
         msg = F.qtatt_tokens_forward(q, k, v, (H, W), (H1, W1), topks, self.num_heads, weight=weight,
                                      attn_type='A' if self.attn_type == 'A' else 'B').view(B, -1, C)
         return self.proj_drop(self.proj(msg))

@@ -56,9 +56,9 @@ class QTAttB(nn.Module):
             raise NotImplementedError('QTAttB rel_pos is not implemented by casmtr_b200')
         n = len(queries)
         out = F.qtatt_forward([_f32c(q) for q in queries], [_f32c(k) for k in keys], [_f32c(v) for v in values],
-                              self.topks, self.nhead, weight=self.weight[:n], attn_type='B')
+                              self.topks, self.nhead, weight=self.weight, attn_type='B')     # soft-max over the WHOLE parameter (:264)
         if self.lepe:    # (m_i + lepe_i) * w_i == m_i * w_i + lepe_i * w_i; the second term is added here (:266-282)
-            w = torch.softmax(self.weight[:n], dim=0)
+            w = torch.softmax(self.weight, dim=0)
             B, C, H, W = values[0].shape
             for i in range(n):
                 lp = self.get_vs[i](values[-(i + 1)])

@@ -47,7 +47,7 @@ def window_positions(idx, H, W, window=5):
     return torch.stack([rows, cols], dim=-1)
 
 
-def cascade_inputs(B, C, h, w, seed=1234, max_shift=4, corrupt=0.1, pad=False):
+def cascade_inputs(B, C, h, w, seed=1234, max_shift=4, corrupt=0.1, pad=False, shifts=None):
     """Structured cascade-stage inputs: feat1 is feat0 rolled by a per-pair integer
     shift plus noise, so the window correlation has a real peak (random features
     would threshold every match away).
@@ -55,11 +55,13 @@ def cascade_inputs(B, C, h, w, seed=1234, max_shift=4, corrupt=0.1, pad=False):
     Returns dict: feat0, feat1 [B,C,h,w]; next_idx01, next_idx10 [B,(h/2*w/2)] int64
     (previous-stage correspondences, ``corrupt`` fraction randomised); pre_conf01
     [B,h/2*w/2] ~U(0,1); topk_pos01/topk_pos10 [B,h/2*w/2,25,2]; shifts [B,2];
-    optional pad masks mask0/mask1 [B,h,w] bool (bottom/right bands)."""
+    optional pad masks mask0/mask1 [B,h,w] bool (bottom/right bands).
+    shifts: optional [B,2] even integer shifts to use instead of drawing them (the same physical motion at another level)."""
     g = _gen(seed)
     hp, wp = h // 2, w // 2
     feat0 = 3.0 * torch.randn(B, C, h, w, generator=g)
-    shifts = torch.randint(-max_shift, max_shift + 1, (B, 2), generator=g) * 2   # even => exact at the previous level
+    drawn = torch.randint(-max_shift, max_shift + 1, (B, 2), generator=g) * 2    # even => exact at the previous level
+    shifts = drawn if shifts is None else shifts.to(torch.int64)
     feat1 = torch.stack([torch.roll(feat0[b], (int(shifts[b, 0]), int(shifts[b, 1])), (1, 2)) for b in range(B)])
     feat1 = feat1 + 0.3 * torch.randn(B, C, h, w, generator=g)
     py, px = torch.meshgrid(torch.arange(hp), torch.arange(wp), indexing='ij')

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CASMTR_VERSION 100          /* 0.1.0 */
+#define CASMTR_VERSION 200          /* 0.2.0: casmtr_qtatt_desc grew flags / concurrent_calls; casmtr_set_concurrency removed */
 #define CASMTR_MAX_LEVELS 4
 
 #define CASMTR_OK 0
@@ -139,14 +139,24 @@ typedef struct {
     int kh[CASMTR_MAX_LEVELS];      /* key/value grid per level */
     int kw[CASMTR_MAX_LEVELS];
     int topks[CASMTR_MAX_LEVELS];   /* the reference's `topks`: [0] = coarsest level */
+    int flags;                      /* CASMTR_QT_* bits, 0 = defaults */
+    int weight_len;                 /* entries of level_weight (QTAttB.weight has `scale` of them, reference :159); the soft-max runs
+                                     * over ALL of them (:264) even when the pyramid is shorter.  0 = `levels`. */
+    int concurrent_calls;           /* launch-geometry hint: independent calls of this shape the caller keeps in flight at once
+                                     * (other streams / graph branches); 0 or 1 = this call runs alone.  Results do not depend on it.
+                                     * Callers that stack the two directions of a layer on the batch dimension (B = 2 x pairs) need
+                                     * no hint: every kernel sizes its grid from B. */
 } casmtr_qtatt_desc;
+
+#define CASMTR_QT_NO_OVERLAP 1      /* casmtr_qtatt_fwd: keep the transposes of the finer levels on the caller's stream */
+#define CASMTR_QT_SIMT_COARSE 2     /* dense coarsest level on the fp32 SIMT kernel instead of the tcgen05 one (A/B, parity tests) */
 
 CASMTR_API size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc);
 
 /* queries/keys/values: HOST arrays of `levels` device pointers, [l] = [B,C,h_l,w_l] NCHW fp32,
  * l = 0 finest (exactly the lists QTAttB.forward receives).
- * level_weight: device [levels], the raw `weight` parameter of QTAttB (softmax over levels is
- *   applied inside, reference :264); ignored (may be NULL) for type A.
+ * level_weight: device [weight_len], the raw `weight` parameter of QTAttB (the softmax over its entries is
+ *   applied inside, reference :264; level i of the processing order uses entry i); ignored (may be NULL) for type A.
  * out: [B, qh[0]*qw[0], nhead, D].
  * topk_idx_out / topk_score_out: optional HOST arrays (or NULL) of `levels` device pointers in
  *   the reference's processing order ([0] = coarsest); entry i, if non-NULL, receives the
@@ -169,27 +179,24 @@ CASMTR_API int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *desc, const floa
                      int64_t *const *topk_idx_out, float *const *topk_score_out,
                      void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
-/* Programmatic dependent launch: when on (default; CASMTR_PDL=0 in the environment turns it off) every hot-path kernel is
- * launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the previous kernel of the
- * stream drains and wait (griddepcontrol.wait) for its completion before touching memory.  Helps back-to-back launches on ONE
- * stream; turn it off when independent calls already overlap on several streams (waiting CTAs hold SM resources the other
- * stream could use).  Returns the previous setting. */
+/* Launch options.  Both are settings of the CALLING THREAD (thread-local, default on), not of the process: a second host thread
+ * is unaffected, and a stream capture records what the capturing thread selected.  Per-call options live in the descriptors
+ * (casmtr_qtatt_desc.flags / .concurrent_calls).
+ *
+ * Programmatic dependent launch (CASMTR_PDL=0 in the environment makes off the default): every hot-path kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the previous kernel of the stream drains
+ * and wait (griddepcontrol.wait) for its completion before touching memory.  Helps back-to-back launches on ONE stream; turn it
+ * off when independent calls already overlap on several streams.  Returns the previous setting of this thread. */
 CASMTR_API int casmtr_set_pdl(int on);
 
-/* Layout / compute overlap inside casmtr_qtatt_fwd: when on (default; CASMTR_OVERLAP=0 in the environment turns it off) the
- * call forks the NCHW -> token-major transposes of all but the coarsest pyramid level onto a library-owned side stream and
- * joins them back before the first fine level, so they run under the coarsest level's kernel.  The call stays fully ordered
- * with respect to the caller's stream (event fork after the caller's prior work, event join before the call's later kernels
- * and anything the caller enqueues afterwards) and can be stream-captured.  Turning it on creates the side streams (2 per
- * device) if they do not exist yet -- do that outside a capture.  Returns the previous setting. */
+/* Layout / compute overlap inside casmtr_qtatt_fwd (CASMTR_OVERLAP=0 in the environment makes off the default): the call forks the
+ * NCHW -> token-major transposes of all but the coarsest pyramid level onto a library-owned side stream and joins them back
+ * before the first fine level, so they run under the coarsest level's kernel.  The call stays fully ordered with respect to the
+ * caller's stream (event fork after the caller's prior work, event join before the call's later kernels and anything the caller
+ * enqueues afterwards) and can be stream-captured; concurrent callers on one device are serialised while they enqueue.  Turning
+ * it on creates the side streams (2 per device) if they do not exist yet -- do that outside a capture.  CASMTR_QT_NO_OVERLAP in
+ * a descriptor switches it off for that call.  Returns the previous setting of this thread. */
 CASMTR_API int casmtr_set_overlap(int on);
-
-/* Launch-geometry hint: the number of independent calls the caller keeps in flight at once (default 1; e.g. 2 when the two
- * directions of a layer run on two streams or in two branches of a CUDA graph).  Kernels that trade per-CTA efficiency against
- * the number of CTAs (the dense coarsest quadtree level: 32-row CTAs stream the K / V tiles half as often as 16-row CTAs but a
- * single call has too few of them to fill 148 SMs) size their grids for the combined work.  Results do not depend on it.
- * Returns the previous value. */
-CASMTR_API int casmtr_set_concurrency(int n);
 
 /* ---------------------------------------------------------------- fused cascade window attention (R5) */
 

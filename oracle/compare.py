@@ -36,9 +36,11 @@ def children_rows(mask, h, w):
     return m.reshape(B, 4 * h * w, nh)
 
 
-def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3):
+def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3, max_tie_frac=0.0):
     """Level by level: identical top-k key sets (fp32 near-ties at the k-th place excepted, see topk_bad_rows),
     scores within 1e-5, and the merged message within `tol` on every (token, head) that does not descend from a tie row.
+    max_tie_frac: allowed fraction of tie-tainted rows.  0 for the committed seeds (they contain no near-tie); full-size random
+    inputs pass a small allowance (a relative gap < 1e-5 at a k-th place happens once in a few thousand rows).
     Returns (max message error on clean rows, fraction of tie-tainted rows)."""
     taint = None                                        # [B, L_i, nh] rows whose candidate sets legitimately differ
     for i, ti in enumerate(tk_idx):
@@ -50,7 +52,7 @@ def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3):
         if i < lv - 1:
             taint = children_rows(taint, gh, gw)
     frac = taint.float().mean().item()
-    assert frac < 0.05, f'{what}: too many tie rows ({frac:.3f})'
+    assert frac <= max_tie_frac, f'{what}: tie rows {frac:.5f} > allowed {max_tie_frac}'
     diff = (out.cpu() - ref).abs().amax(dim=-1)          # [B, L, nh]
     err = diff[~taint].max().item()
     assert err < tol, f'{what}: message differs from the oracle by {err}'

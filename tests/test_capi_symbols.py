@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(handle, name), f'{name} declared in include/casmtr_b200.h but not exported'
     assert set(_lib.SIGNATURES) == set(declared_symbols())      # the ctypes table covers the whole header
-    assert _lib.lib().casmtr_version() == 100
+    assert _lib.lib().casmtr_version() == 200
 
 
 def test_argument_validation_needs_no_gpu():
@@ -128,8 +128,15 @@ def test_host_mirror_of_the_relative_pe_module_needs_no_gpu():
 def test_tuning_switches_round_trip():
     from casmtr_b200 import _lib
     lib = _lib.lib()
-    prev = lib.casmtr_set_concurrency(2)
-    assert lib.casmtr_set_concurrency(prev) == 2 and lib.casmtr_set_concurrency(0) == prev and lib.casmtr_set_concurrency(prev) == 1
+    prev = lib.casmtr_set_pdl(0)
+    assert lib.casmtr_set_pdl(prev) == 0 and lib.casmtr_set_pdl(prev) == prev
+    # the switches belong to the calling thread: another thread still sees the default
+    import threading
+    seen = []
+    lib.casmtr_set_pdl(0)
+    t = threading.Thread(target=lambda: seen.append(lib.casmtr_set_pdl(1)))
+    t.start(); t.join()
+    assert seen == [1] and lib.casmtr_set_pdl(prev) == 0
 
 
 def test_header_is_plain_c_and_links(tmp_path):
