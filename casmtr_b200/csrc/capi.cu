@@ -282,11 +282,18 @@ struct QtattBuffers {
     float *wsm;                                                                    // softmax of the level weights
     int *tk_idx[CASMTR_MAX_LEVELS];
     float *tk_sc[CASMTR_MAX_LEVELS];
+    float *tc_ws;                                                                  // scratch of the tensor-core coarsest level (or NULL)
 };
 
 static void carve_qtatt(const casmtr_qtatt_desc *d, Workspace &ws, QtattBuffers &bf) {
     const size_t C = (size_t)d->nhead * d->D;
     bf.wsm = ws.take<float>(CASMTR_MAX_LEVELS);
+    {
+        const int lc = d->levels - 1;
+        const int Sq = d->qh[lc] * d->qw[lc], Sk = d->kh[lc] * d->kw[lc];
+        const bool tc = !(d->flags & CASMTR_QT_SIMT_COARSE) && d->D == 32 && coarse_tc_applicable(Sq, Sk, d->topks[0]);
+        bf.tc_ws = tc ? ws.take<float>(coarse_tc_workspace_floats(d->B, Sq, Sk, (int)C)) : nullptr;
+    }
     for (int l = 0; l < d->levels; ++l) {
         bf.q[l] = ws.take<float>((size_t)d->B * d->qh[l] * d->qw[l] * C);
         bf.k[l] = ws.take<float>((size_t)d->B * d->kh[l] * d->kw[l] * C);
@@ -433,7 +440,7 @@ static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf,
             cp.acc = dst; cp.topk_idx = bf.tk_idx[0]; cp.topk_score = bf.tk_sc[0];
             cp.level_weight = wts; cp.levels = d->levels; cp.n_weights = d->weight_len > 0 ? d->weight_len : d->levels; cp.wsm = wts ? bf.wsm : nullptr;
             cp.B = d->B; cp.Sq = d->qh[l] * d->qw[l]; cp.Sk = d->kh[l] * d->kw[l];
-            cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type;
+            cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type; cp.tc_ws = bf.tc_ws;
             rc = launch_qtatt_coarse(cp, stream);
         } else {
             FineParams fp;

@@ -40,9 +40,14 @@ struct CoarseParams {
     int levels, n_weights;      // pyramid levels; entries of level_weight the soft-max runs over (>= levels)
     int B, Sq, Sk, nh, topk;
     int type_a;
+    float *tc_ws;               // coarse_tc_workspace_floats() of scratch for the tensor-core kernel, or NULL: fp32 SIMT kernel
 };
 size_t coarse_smem_bytes(int Sk);
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
+// qtatt_coarse_tc.cu: the same level with both contractions on tcgen05 (Sq, Sk >= 64, Sk <= 1344)
+bool coarse_tc_applicable(int Sq, int Sk, int topk);
+size_t coarse_tc_workspace_floats(int B, int Sq, int Sk, int C);
+int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream);
 
 // ---- relative position bias of the cascade cross attention, computed where it is consumed
 // (CascadeFeatureTransformer.get_relative_pe, src/model/modules/transformer.py:473-509; casmtr_relpe_desc)

@@ -228,29 +228,43 @@ int launch_window_idx(const int64_t *next_idx, int64_t *pos, size_t rows, int H,
 }
 
 // internal [B,L,nh,k] int32 / fp32  ->  reference [B,L,k,nh] int64 / fp32
+// Internal top-k lists ([n_tok, nh, k] int32 / fp32, in whatever order the level kernels emit them) -> the reference's API
+// layout [n_tok, k, nh] int64 / fp32 SORTED by descending score like torch.topk(sorted=True) (ties: lower key index first).
+// One warp per (token, head); rank counting over the k <= 32 entries.  Off the hot path: only callers that ask for the lists pay.
 __global__ void topk_to_api_kernel(const int *__restrict__ idx, const float *__restrict__ score,
                                    int64_t *__restrict__ idx_out, float *__restrict__ score_out,
                                    size_t n_tok, int nh, int k) {
     pdl_sync();
-    const size_t total = n_tok * nh * k;
-    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
-        const int h = (int)(o % nh);
-        const int kk = (int)((o / nh) % k);
-        const size_t tok = o / ((size_t)nh * k);
-        const size_t in = (tok * nh + h) * k + kk;
-        if (idx_out) idx_out[o] = idx[in];
-        if (score_out) score_out[o] = score[in];
+    const int lane = threadIdx.x & 31;
+    const size_t n_items = n_tok * nh;
+    for (size_t it = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; it < n_items; it += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const size_t tok = it / nh;
+        const int h = (int)(it - tok * nh);
+        const float s = lane < k ? score[it * k + lane] : -INFINITY;
+        const int ix = lane < k ? idx[it * k + lane] : 0x7fffffff;
+        int rank = 0;
+        for (int l = 0; l < k; ++l) {
+            const float so = __shfl_sync(FULL_MASK, s, l);
+            const int io = __shfl_sync(FULL_MASK, ix, l);
+            rank += (so > s) || (so == s && io < ix);
+        }
+        if (lane < k) {
+            const size_t o = (tok * k + rank) * nh + h;
+            if (idx_out) idx_out[o] = ix;
+            if (score_out) score_out[o] = s;
+        }
     }
 }
 
 int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
                        size_t n_tok, int nh, int k, cudaStream_t stream) {
-    const size_t total = n_tok * nh * k;
-    if (total == 0) return CASMTR_OK;
-    int blocks = (int)((total + 255) / 256);
+    const size_t total = n_tok * nh;            // one warp each
+    if (total == 0 || k <= 0) return CASMTR_OK;
+    CASMTR_REQUIRE(k <= 32, CASMTR_E_UNSUPPORTED, "top-k export: k=%d > 32", k);
+    size_t blocks = (total + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     LaunchScope ls(CASMTR_K_LAYOUT, stream);
-    launch_k(topk_to_api_kernel, blocks, 256, 0, stream, idx, score, idx_out, score_out, n_tok, nh, k);
+    launch_k(topk_to_api_kernel, (unsigned)blocks, 256, 0, stream, idx, score, idx_out, score_out, n_tok, nh, k);
     CASMTR_CHECK_LAUNCH("topk_to_api_kernel");
     return CASMTR_OK;
 }

@@ -491,6 +491,7 @@ size_t smem_bytes(int Sk, int rows) {
 size_t coarse_smem_bytes(int Sk) { return smem_bytes(Sk, 8); }
 
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream) {
+    if (p.tc_ws != nullptr && coarse_tc_applicable(p.Sq, p.Sk, p.topk)) return launch_qtatt_coarse_tc(p, p.tc_ws, stream);
     // 32-row CTAs are the efficient shape (every lane owns a row).  With too few of them to give every SM two, halve the
     // rows per CTA (lane groups split the tokens).  Measured at 832^2, B = 1 (676 rows x 8 heads): 32 rows 76 us, 16 rows
     // 58 us, 8 rows 64 us (every CTA streams all K and V tiles, so below 16 rows the tile traffic and barriers dominate).

@@ -36,11 +36,12 @@ def children_rows(mask, h, w):
     return m.reshape(B, 4 * h * w, nh)
 
 
-def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3, max_tie_frac=0.0):
+def check_qtatt_levels(out, tk_idx, tk_sc, ref, aux, h, w, lv, what, tol=1e-3, max_tie_frac=1e-3):
     """Level by level: identical top-k key sets (fp32 near-ties at the k-th place excepted, see topk_bad_rows),
     scores within 1e-5, and the merged message within `tol` on every (token, head) that does not descend from a tie row.
-    max_tie_frac: allowed fraction of tie-tainted rows.  0 for the committed seeds (they contain no near-tie); full-size random
-    inputs pass a small allowance (a relative gap < 1e-5 at a k-th place happens once in a few thousand rows).
+    max_tie_frac: allowed fraction of tie-tainted rows (rows whose k-th and (k+1)-th scores differ by < 1e-5 relative, plus
+    their descendants).  Random logits produce such a gap about once in a few thousand rows whatever the summation order, so
+    the default is 1e-3 (round 1 allowed 5e-2); the golden fixtures and smoke() pass 0: they contain no near-tie.
     Returns (max message error on clean rows, fraction of tie-tainted rows)."""
     taint = None                                        # [B, L_i, nh] rows whose candidate sets legitimately differ
     for i, ti in enumerate(tk_idx):
