@@ -32,7 +32,7 @@ class ExtractDesc(C.Structure):
                 ('nms_window', C.c_int), ('test_thr', C.c_float), ('border_rm', C.c_int), ('double_check', C.c_int),
                 ('n_pre', C.c_int), ('pre_conf', C.c_void_p * 2), ('pre_h', C.c_int * 2), ('pre_w', C.c_int * 2),
                 ('pre_thr', C.c_float * 2), ('pad_mask0', C.c_void_p), ('pad_mask1', C.c_void_p),
-                ('scale', C.c_float), ('scale0', C.c_void_p), ('scale1', C.c_void_p)]
+                ('scale', C.c_float), ('scale0', C.c_void_p), ('scale1', C.c_void_p), ('coarse_mode', C.c_int)]
 
 
 class RelpeDesc(C.Structure):
@@ -85,6 +85,8 @@ SIGNATURES = {
                                 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_coarse_match_masked_fwd': (C.c_int, [c_float_p, c_float_p, c_u8_p, c_u8_p, C.c_float, c_float_p, c_i64_p, c_float_p, c_i64_p]
                                        + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_coarse_match_mutual_fwd': (C.c_int, [c_float_p, c_float_p, c_u8_p, c_u8_p, C.c_float, c_float_p, c_i64_p, c_float_p, c_i64_p,
+                                                 c_float_p, c_i64_p, c_i64_p] + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_match_extract_workspace_bytes': (C.c_size_t, [C.POINTER(ExtractDesc)]),
     'casmtr_match_extract': (C.c_int, [C.POINTER(ExtractDesc), c_float_p, c_i64_p, c_i64_p, c_u8_p, c_i64_p, c_i64_p, c_i64_p,
                                        c_float_p, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

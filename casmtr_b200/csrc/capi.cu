@@ -678,6 +678,20 @@ int casmtr_coarse_match_masked_fwd(const float *feat0, const float *feat1, const
                                workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int casmtr_coarse_match_mutual_fwd(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1, float temperature,
+                                   float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                                   float *mconf_row, int64_t *midx_row, int64_t *midx_col,
+                                   int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream) {
+    CASMTR_REQUIRE(B >= 1 && L0 > 0 && L1 > 0 && C > 0, CASMTR_E_INVALID, "coarse_match_mutual: bad sizes");
+    CASMTR_REQUIRE((mask0 == nullptr) == (mask1 == nullptr), CASMTR_E_INVALID, "coarse_match_mutual: give both masks or neither");
+    CASMTR_REQUIRE(feat0 && feat1 && next_conf01 && next_idx01 && next_conf10 && next_idx10 && mconf_row && midx_row && midx_col && workspace,
+                   CASMTR_E_INVALID, "coarse_match_mutual: null pointer");
+    CASMTR_REQUIRE(temperature > 0.f, CASMTR_E_INVALID, "coarse_match_mutual: temperature must be positive");
+    CASMTR_REQUIRE(2 * B <= 65535, CASMTR_E_UNSUPPORTED, "coarse_match_mutual: batch too large");
+    return launch_coarse_match(feat0, feat1, mask0, mask1, temperature, next_conf01, next_idx01, next_conf10, next_idx10, B, L0, L1, C,
+                               workspace, workspace_bytes, (cudaStream_t)stream, mconf_row, midx_row, midx_col);
+}
+
 // ------------------------------------------------------------------------------------------------ extraction
 static int check_extract_desc(const casmtr_extract_desc *d) {
     CASMTR_REQUIRE(d != nullptr, CASMTR_E_INVALID, "match_extract: null descriptor");

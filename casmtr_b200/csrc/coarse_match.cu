@@ -37,6 +37,10 @@ struct CoarseStatParams {
     float scale_log2;           // log2(e) / (C * temperature)
     const uint32_t *mbits[2];   // padding masks of image 0 / 1 packed 32 tokens per word ([B][mwords]), or NULL (reference :64-65)
     int mwords[2];
+    // second pass (mutual nearest neighbours of conf = softmax_i * softmax_j, reference :68, :122): per direction the log-sum-exp
+    // (base 2) of every COLUMN of that direction's similarity, [B][Lmax]; the kernel then reduces 2 * sim - lse_col over each row
+    const float *cbias[2];
+    float *lse;                 // [2][B * Lmax] out of the first merge: log2-sum-exp of every row of direction 0 / 1
 };
 
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
@@ -84,6 +88,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <bool BIAS>
 __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_constant__ CoarseMaps maps, CoarseStatParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 128B-swizzled TMA tiles want 1024-byte alignment; an offset
@@ -165,6 +170,8 @@ __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_co
         float m = -INFINITY, l = 0.f;
         int arg = 0;
         const uint32_t *cmask = p.mbits[1 - dir] ? p.mbits[1 - dir] + (size_t)b * p.mwords[1 - dir] : nullptr;
+        const float *cb = BIAS ? p.cbias[dir] + (size_t)b * p.Lmax : nullptr;
+        const float sc = BIAS ? 2.f * p.scale_log2 : p.scale_log2;
         for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
             const int a = it & 1;
             mbar_wait(tfull + a, (it >> 1) & 1);
@@ -178,15 +185,31 @@ __global__ void __launch_bounds__(192, 1) coarse_rowstats_kernel(const __grid_co
                 const uint32_t cbits = (cmask != nullptr && col0 < Lc) ? __ldg(cmask + (col0 >> 5)) : 0xffffffffu;
                 float cm = -INFINITY;
                 int ca = 0;
+                if (BIAS) {                                       // log2 conf[i, j] + lse_row_i = 2 sim - lse_col_j: only max / arg-max are needed
+                    float bias[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = (col0 + i < Lc && ((cbits >> i) & 1u)) ? v[i] * p.scale_log2 : -INFINITY;
-                    if (v[i] > cm) { cm = v[i]; ca = i; }
-                }
-                if (cm > m) { l *= exp2f(m - cm); m = cm; arg = col0 + ca; }
-                if (m > -INFINITY) {
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col0 + 4 * i4 < Lc) t4 = ldg4(cb + col0 + 4 * i4);      // Lmax is padded to a multiple of 4
+                        bias[4 * i4] = t4.x; bias[4 * i4 + 1] = t4.y; bias[4 * i4 + 2] = t4.z; bias[4 * i4 + 3] = t4.w;
+                    }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) l += exp2f(v[i] - m);
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = (col0 + i < Lc && ((cbits >> i) & 1u)) ? fmaf(v[i], sc, -bias[i]) : -INFINITY;
+                        if (v[i] > cm) { cm = v[i]; ca = i; }
+                    }
+                    if (cm > m) { m = cm; arg = col0 + ca; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = (col0 + i < Lc && ((cbits >> i) & 1u)) ? v[i] * sc : -INFINITY;
+                        if (v[i] > cm) { cm = v[i]; ca = i; }
+                    }
+                    if (cm > m) { l *= exp2f(m - cm); m = cm; arg = col0 + ca; }
+                    if (m > -INFINITY) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) l += exp2f(v[i] - m);
+                    }
                 }
             }
             tc_fence_before();
@@ -243,6 +266,32 @@ __global__ void coarse_merge_kernel(CoarseStatParams p, float *conf01, int64_t *
     const bool dead = m == -INFINITY || (p.mbits[dir] && !((p.mbits[dir][(size_t)b * p.mwords[dir] + (row >> 5)] >> (row & 31)) & 1u));
     (dir ? conf10 : conf01)[i] = dead ? 1.0f / (float)p.L[1 - dir] : 1.0f / l;
     (dir ? idx10 : idx01)[i] = dead ? 0 : arg;
+    // log2-sum-exp of the row, for the second pass; +inf marks a dead row (its conf is 0: never a mutual match)
+    if (p.lse) p.lse[((size_t)dir * p.B + b) * p.Lmax + row] = dead ? INFINITY : m + log2f(l);
+}
+
+// second merge: row maximum / arg-max of conf = softmax_i * softmax_j from the partial maxima of 2 sim - lse_col:
+//   mconf_row[i] = max_j conf[i, j] = 2^(max_j(2 sim_ij - lse_col_j) - lse_row_i),  midx_row[i] = its arg-max; midx_col likewise over i
+__global__ void coarse_merge2_kernel(CoarseStatParams p, float *mconf_row, int64_t *midx_row, int64_t *midx_col) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int dir = blockIdx.y;
+    const int Lr = p.L[dir];
+    if (i >= (size_t)p.B * Lr) return;
+    const int b = (int)(i / Lr), row = (int)(i % Lr);
+    float m = -INFINITY;
+    int arg = 0;
+    for (int s = 0; s < p.nsplit; ++s) {
+        const size_t o = ((size_t)(dir * p.nsplit + s) * p.B + b) * p.Lmax + row;
+        if (p.pmax[o] > m) { m = p.pmax[o]; arg = p.parg[o]; }
+    }
+    const float lse = p.lse[((size_t)dir * p.B + b) * p.Lmax + row];
+    const bool dead = m == -INFINITY || lse == INFINITY;
+    if (dir == 0) {
+        mconf_row[i] = dead ? 0.f : exp2f(m - lse);
+        midx_row[i] = dead ? 0 : arg;
+    } else {
+        midx_col[i] = dead ? -1 : arg;              // -1: no row points back to a dead column
+    }
 }
 
 // uint8 mask [B, L] -> one bit per token, 32 tokens per word: a warp per word
@@ -288,7 +337,8 @@ int pick_nsplit(int B, int L0, int L1) {
 
 size_t coarse_match_workspace(int B, int L0, int L1, int C) {
     Workspace ws(nullptr, 0);
-    const int Lmax = L0 > L1 ? L0 : L1, ns = pick_nsplit(B, L0, L1);
+    const int Lmax = ((L0 > L1 ? L0 : L1) + 3) / 4 * 4, ns = pick_nsplit(B, L0, L1);
+    ws.take<float>((size_t)2 * B * Lmax);
     ws.take<float>((size_t)B * L0 * C);
     ws.take<float>((size_t)B * L1 * C);
     ws.take<float>((size_t)2 * ns * B * Lmax);
@@ -301,13 +351,17 @@ size_t coarse_match_workspace(int B, int L0, int L1, int C) {
 
 int launch_coarse_match(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1, float temperature,
                         float *conf01, int64_t *idx01, float *conf10,
-                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                        float *mconf_row, int64_t *midx_row, int64_t *midx_col) {
     CASMTR_REQUIRE(C % BK == 0 && C >= BK, CASMTR_E_UNSUPPORTED, "coarse_match: C=%d must be a multiple of %d", C, BK);
     CASMTR_REQUIRE((((uintptr_t)feat0 | (uintptr_t)feat1) & 15) == 0, CASMTR_E_INVALID, "coarse_match: features must be 16-byte aligned");
     Workspace ws(workspace, workspace_bytes);
-    const int Lmax = L0 > L1 ? L0 : L1, ns = pick_nsplit(B, L0, L1);
+    const int Lmax = ((L0 > L1 ? L0 : L1) + 3) / 4 * 4, ns = pick_nsplit(B, L0, L1);
+    float *lse = ws.take<float>((size_t)2 * B * Lmax);
     float *lo0 = ws.take<float>((size_t)B * L0 * C), *lo1 = ws.take<float>((size_t)B * L1 * C);
     CoarseStatParams p;
+    p.lse = mconf_row ? lse : nullptr;
+    p.cbias[0] = p.cbias[1] = nullptr;
     p.pmax = ws.take<float>((size_t)2 * ns * B * Lmax);
     p.psum = ws.take<float>((size_t)2 * ns * B * Lmax);
     p.parg = ws.take<int>((size_t)2 * ns * B * Lmax);
@@ -348,19 +402,35 @@ int launch_coarse_match(const float *feat0, const float *feat1, const uint8_t *m
     static PerDeviceOnce once;
     const int dev = PerDeviceOnce::device();
     if (!once.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(coarse_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(coarse_rowstats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(coarse_rowstats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
         once.mark(dev);
     }
+    const int Lgrid = L0 > L1 ? L0 : L1;
     {
         LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
-        coarse_rowstats_kernel<<<dim3((Lmax + BM - 1) / BM, ns, 2 * B), 192, smem, stream>>>(maps, p);
+        coarse_rowstats_kernel<false><<<dim3((Lgrid + BM - 1) / BM, ns, 2 * B), 192, smem, stream>>>(maps, p);
         CASMTR_CHECK_LAUNCH("coarse_rowstats_kernel");
     }
     {
         LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
-        coarse_merge_kernel<<<dim3(((size_t)B * Lmax + 255) / 256, 2), 256, 0, stream>>>(p, conf01, idx01, conf10, idx10);
+        coarse_merge_kernel<<<dim3(((size_t)B * Lgrid + 255) / 256, 2), 256, 0, stream>>>(p, conf01, idx01, conf10, idx10);
         CASMTR_CHECK_LAUNCH("coarse_merge_kernel");
+    }
+    if (mconf_row == nullptr) return CASMTR_OK;
+    // second pass: the columns of direction d are the rows of direction 1 - d
+    p.cbias[0] = lse + (size_t)B * Lmax;
+    p.cbias[1] = lse;
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        coarse_rowstats_kernel<true><<<dim3((Lgrid + BM - 1) / BM, ns, 2 * B), 192, smem, stream>>>(maps, p);
+        CASMTR_CHECK_LAUNCH("coarse_rowstats_kernel (mutual pass)");
+    }
+    {
+        LaunchScope ls(CASMTR_K_COARSE_MATCH, stream);
+        coarse_merge2_kernel<<<dim3(((size_t)B * Lgrid + 255) / 256, 2), 256, 0, stream>>>(p, mconf_row, midx_row, midx_col);
+        CASMTR_CHECK_LAUNCH("coarse_merge2_kernel");
     }
     return CASMTR_OK;
 }

@@ -81,7 +81,8 @@ __device__ __forceinline__ bool keep_token(const ExtractArgs &a, int b, int i) {
         const int hs1 = a.valid1 ? a.valid1[2 * b] : d.h1, ws1 = a.valid1 ? a.valid1[2 * b + 1] : d.w1;
         if (y < bd || x < bd || y >= hs0 - bd || x >= ws0 - bd) return false;
         const long long ty = j / d.w1, tx = j - ty * d.w1;
-        if (tx < bd || tx > ws1 - bd || ty < bd || ty > hs1 - bd) return false;
+        if (d.coarse_mode ? (tx < bd || tx >= ws1 - bd || ty < bd || ty >= hs1 - bd)      // mask_border: symmetric (coarse_matching.py:116-119)
+                          : (tx < bd || tx > ws1 - bd || ty < bd || ty > hs1 - bd)) return false;
     }
     // 4. mutual nearest neighbour
     if (d.double_check) {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(1024) extract_scan_kernel(ExtractArgs a, int n
     }
     if (threadIdx.x == 0) {
         a.total[0] = carry;
-        const int emitted = carry == 0 ? a.d.B : carry;        // "if mask.sum() == 0: mask[:, 0] = True" (:254-255)
+        const int emitted = (carry == 0 && !a.d.coarse_mode) ? a.d.B : carry;        // "if mask.sum() == 0: mask[:, 0] = True" (:254-255); the 1/8 stage has no such fallback
         a.total[1] = emitted;
         *count_out = emitted;
     }
@@ -182,6 +183,10 @@ __global__ void __launch_bounds__(BLK) extract_emit_kernel(ExtractArgs a, EmitOu
     const size_t n = (size_t)a.d.B * L0;
     const size_t o = blockIdx.x * (size_t)BLK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.total[0] == 0 && a.d.coarse_mode) {                  // CoarseMatching: an empty list stays empty
+        if (o < n && e.mask_out) e.mask_out[o] = 0;
+        return;
+    }
     if (a.total[0] == 0) {                                     // fallback: element 0 of every sample (:254-255)
         if (o < n && e.mask_out) e.mask_out[o] = 0;            // mask_out reports the flags BEFORE the fallback
         if (o < n && (o % L0) == 0) {

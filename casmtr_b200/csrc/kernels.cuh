@@ -157,7 +157,8 @@ int launch_cascade_match_tile(const MatchParams &p, cudaStream_t stream);
 // ---- coarse_match.cu: dense dual-softmax row / column statistics on tcgen05
 size_t coarse_match_workspace(int B, int L0, int L1, int C);
 int launch_coarse_match(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1, float temperature, float *conf01, int64_t *idx01, float *conf10,
-                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                        int64_t *idx10, int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                        float *mconf_row = nullptr, int64_t *midx_row = nullptr, int64_t *midx_col = nullptr);
 
 // ---- extract.cu
 int launch_match_extract(const casmtr_extract_desc &d, const float *next_conf01, const int64_t *next_idx01,

@@ -415,10 +415,12 @@ def cascade_match_forward(feat0, feat1, idx01, idx10, mask0=None, mask1=None, te
     return o
 
 
-def coarse_match_forward(feat0, feat1, temperature=0.1, mask0=None, mask1=None):
+def coarse_match_forward(feat0, feat1, temperature=0.1, mask0=None, mask1=None, mutual=False):
     """Dense dual-softmax statistics (tcgen05): feat0 [B,L0,C], feat1 [B,L1,C] -> dict next_conf01 [B,L0], next_idx01 [B,L0]
     (int64), next_conf10 [B,L1], next_idx10 [B,L1]; the L0 x L1 similarity matrix is never materialised.
-    mask0 [B,L0] / mask1 [B,L1] (bool, both or neither): padding masks as in the reference's masked_fill_(-1e9) (padded rows: uniform soft-max, i.e. 1 / columns and index 0)."""
+    mask0 [B,L0] / mask1 [B,L1] (bool, both or neither): padding masks as in the reference's masked_fill_(-1e9) (padded rows: uniform soft-max, i.e. 1 / columns and index 0).
+    mutual=True adds mconf_row [B,L0] (row maximum of conf = softmax_i * softmax_j), midx_row [B,L0] and midx_col [B,L1] (its row /
+    column arg-maxima, int64): what get_coarse_match's mutual-nearest-neighbour test needs (casmtr_coarse_match_mutual_fwd)."""
     _chk(feat0, 'feat0', torch.float32), _chk(feat1, 'feat1', torch.float32)
     B, L0, Cc = feat0.shape
     L1 = feat1.shape[1]
@@ -435,6 +437,14 @@ def coarse_match_forward(feat0, feat1, temperature=0.1, mask0=None, mask1=None):
     with torch.cuda.device(dev):
         nbytes = lib().casmtr_coarse_match_workspace_bytes(B, L0, L1, Cc)
         ws = _workspace(nbytes, dev)
+        if mutual:
+            o.update({'mconf_row': torch.empty(B, L0, dtype=torch.float32, device=dev), 'midx_row': torch.empty(B, L0, dtype=torch.int64, device=dev),
+                      'midx_col': torch.empty(B, L1, dtype=torch.int64, device=dev)})
+            check(lib().casmtr_coarse_match_mutual_fwd(_ptr(feat0), _ptr(feat1), _ptr(mask0), _ptr(mask1), float(temperature),
+                                                       _ptr(o['next_conf01']), _ptr(o['next_idx01']), _ptr(o['next_conf10']), _ptr(o['next_idx10']),
+                                                       _ptr(o['mconf_row']), _ptr(o['midx_row']), _ptr(o['midx_col']), B, L0, L1, Cc,
+                                                       _ptr(ws), ws.numel(), _stream(feat0)), 'casmtr_coarse_match_mutual_fwd')
+            return o
         check(lib().casmtr_coarse_match_masked_fwd(_ptr(feat0), _ptr(feat1), _ptr(mask0), _ptr(mask1), float(temperature),
                                                    _ptr(o['next_conf01']), _ptr(o['next_idx01']),
                                                    _ptr(o['next_conf10']), _ptr(o['next_idx10']), B, L0, L1, Cc, _ptr(ws), ws.numel(),
@@ -444,7 +454,7 @@ def coarse_match_forward(feat0, feat1, temperature=0.1, mask0=None, mask1=None):
 
 def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_thr, border_rm, nms_window=None,
                   pre_confs=(), pre_thrs=(), double_check=True, pad_mask0=None, pad_mask1=None,
-                  scale0=None, scale1=None, defer=False):
+                  scale0=None, scale1=None, defer=False, coarse_mode=False):
     """NMS / thresholds / border / mutual check / ordered compaction.  Same keyword surface as
     oracle.cascade.extract_matches.  One host sync (the match count), like the reference's torch.where.
     defer=True skips that sync (CUDA-graph capture): the result holds full-capacity buffers plus the device-side
@@ -456,6 +466,7 @@ def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_
     d.B, (d.h0, d.w0), (d.h1, d.w1) = B, hw0, hw1
     d.nms_window = 0 if nms_window is None else int(nms_window)
     d.test_thr, d.border_rm, d.double_check = float(test_thr), int(border_rm), int(bool(double_check))
+    d.coarse_mode = int(bool(coarse_mode))        # CoarseMatching.get_coarse_match: symmetric target border, no empty-list fallback
     keep = []
     d.n_pre = len(pre_confs)
     if d.n_pre > 2 or len(pre_thrs) < d.n_pre:
@@ -478,7 +489,7 @@ def match_extract(next_conf01, next_idx01, next_idx10, hw0, hw1, hw0_i, *, test_
         s1 = _chk(scale1.to(torch.float32).contiguous(), 'scale1', torch.float32)
         keep.append(s1)
         d.scale1 = s1.data_ptr()
-    cap = B * L0
+    cap = max(B * L0, B)
     mask = torch.empty(B, L0, dtype=torch.uint8, device=dev)
     ids = torch.empty(3, cap, dtype=torch.int64, device=dev)
     mconf = torch.empty(cap, dtype=torch.float32, device=dev)

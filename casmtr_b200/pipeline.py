@@ -92,7 +92,10 @@ class Workload:
             self.stages.append(s)
         self.window, self.fine_ww = 5, 25
         last = self.stages[-1]
-        self.fine_cap = max(64, (last['h'] * last['w'] // 4)) * pairs     # windows pre-generated for FineMatching
+        # windows pre-generated for FineMatching: a 5x5 NMS keeps at most one token in 9 (in practice ~1 in 40); threshold-only
+        # extraction (indoor config) can keep every token
+        nms = last['cas']['post_config']['method'] == 'maxpool_nms'
+        self.fine_cap = max(64, last['h'] * last['w'] // (4 if nms else 1)) * pairs
 
     # call counts per pair in the reference's (un-stacked) terms
     @property

@@ -311,6 +311,18 @@ CASMTR_API int casmtr_coarse_match_masked_fwd(const float *feat0, const float *f
                             float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
                             int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* The same plus what CoarseMatching.get_coarse_match needs (reference :91-153; the `temp_outputs` of a stage-1 model read its match
+ * list, cascade_model_stage3.py:71-74,146-147): the row maxima / arg-maxima of conf = softmax_i(sim) * softmax_j(sim) (:68) and its
+ * column arg-maxima, from a second tcgen05 pass over the similarity (2 sim - lse_col reduced over every row), again without the matrix:
+ *   mconf_row [B,L0] = max_j conf[i,j],  midx_row [B,L0] = argmax_j conf[i,j],  midx_col [B,L1] = argmax_i conf[i,j]  (int64; -1 for a
+ *   fully padded column).  (i, j) is a mutual nearest neighbour (:122) iff midx_row[i] == j and midx_col[j] == i; feed the three arrays to
+ *   casmtr_match_extract with coarse_mode = 1, test_thr = thr, double_check = 1 for the ordered match list.  Same workspace. */
+CASMTR_API int casmtr_coarse_match_mutual_fwd(const float *feat0, const float *feat1, const uint8_t *mask0, const uint8_t *mask1,
+                            float temperature,
+                            float *next_conf01, int64_t *next_idx01, float *next_conf10, int64_t *next_idx10,
+                            float *mconf_row, int64_t *midx_row, int64_t *midx_col,
+                            int B, int L0, int L1, int C, void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
 /* ---------------------------------------------------------------- NMS + match extraction (R7) */
 
 typedef struct {
@@ -328,6 +340,10 @@ typedef struct {
     float scale;                    /* hw0_i[0] / h0 (cascade_matching.py:317) */
     const float *scale0;            /* NULL or device [B,2] */
     const float *scale1;            /* NULL or device [B,2] */
+    int coarse_mode;                /* 0: CascadeMatching.get_coarse_match.  1: CoarseMatching.get_coarse_match (coarse_matching.py:
+                                     * 91-153): the border is removed symmetrically on the target grid as well (row / col >= size - b,
+                                     * mask_border, cascade_functions.py:82-100, where the cascade helper tests > size - b) and an empty
+                                     * result stays empty (no "keep element 0" fallback) */
 } casmtr_extract_desc;
 
 CASMTR_API size_t casmtr_match_extract_workspace_bytes(const casmtr_extract_desc *desc);

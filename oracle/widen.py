@@ -1,6 +1,7 @@
 """CPU restatements of the SURVEY section 8f "next" rows (test infrastructure only -- see oracle/__init__.py).
 
   coarse_match_stats        src/model/functions/coarse_matching.py:60-75   (CoarseMatching.forward, inference statistics)
+  coarse_matches            src/model/functions/coarse_matching.py:91-153  (CoarseMatching.get_coarse_match, inference)
   fine_windows              src/model/functions/fine_matching.py:47-66     (CascadeFinePreprocess.forward)
   quadtree_attention_layer  src/model/modules/quadtree_attention.py:68-99  (QuadtreeAttention.forward, type A / B)
   cascade_attention_layer   src/model/modules/quadtree_attention.py:152-171 (CascadeQuadtreeAttention.forward)
@@ -25,6 +26,48 @@ def coarse_match_stats(feat0, feat1, temperature, dtype=torch.float32, mask0=Non
     c01, i01 = p01.max(dim=2)
     c10, i10 = p10.max(dim=1)
     return c01, i01, c10, i10, sim
+
+
+def coarse_matches(feat0, feat1, temperature, thr, border_rm, hw0, hw1, hw0_i, mask0=None, mask1=None, pad_mask0=None, pad_mask1=None,
+                   scale0=None, scale1=None):
+    """CoarseMatching.get_coarse_match, inference (coarse_matching.py:91-153) on the dense confidence matrix conf = softmax_i * softmax_j
+    (:66-68).  :113 conf > thr; :114-119 border removal on the source AND target grids (mask_border: rows / cols < b or >= size - b;
+    mask_border_with_padding when pad_mask0 / pad_mask1 [B,h,w] are given: the valid extents per sample replace the sizes);
+    :122 mutual nearest neighbours (conf equals its row maximum and its column maximum); :126-129 at most one match per row, in
+    torch.where order; :135-139 keypoints.  Returns dict b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c."""
+    from .cascade import valid_extent
+    C = feat0.shape[-1]
+    sim = torch.einsum('nlc,nsc->nls', feat0 / C ** 0.5, feat1 / C ** 0.5) / temperature
+    if mask0 is not None:
+        sim = sim.masked_fill(~(mask0[..., None] * mask1[:, None]).bool(), -1e9)
+    conf = torch.softmax(sim, 1) * torch.softmax(sim, 2)
+    B, L, S = conf.shape
+    (h0, w0), (h1, w1) = hw0, hw1
+    mask = conf > thr
+    b = border_rm
+    if b > 0:
+        y0, x0 = torch.arange(L) // w0, torch.arange(L) % w0
+        y1, x1 = torch.arange(S) // w1, torch.arange(S) % w1
+        if pad_mask0 is None:
+            bad0 = ((y0 < b) | (x0 < b) | (y0 >= h0 - b) | (x0 >= w0 - b)).unsqueeze(0).expand(B, L)
+            bad1 = ((y1 < b) | (x1 < b) | (y1 >= h1 - b) | (x1 >= w1 - b)).unsqueeze(0).expand(B, S)
+        else:
+            h0s, w0s = valid_extent(pad_mask0)
+            h1s, w1s = valid_extent(pad_mask1)
+            bad0 = (y0 < b)[None] | (x0 < b)[None] | (y0[None] >= h0s[:, None] - b) | (x0[None] >= w0s[:, None] - b)
+            bad1 = (y1 < b)[None] | (x1 < b)[None] | (y1[None] >= h1s[:, None] - b) | (x1[None] >= w1s[:, None] - b)
+        mask = mask & ~bad0[:, :, None] & ~bad1[:, None, :]
+    mask = mask & (conf == conf.max(dim=2, keepdim=True)[0]) & (conf == conf.max(dim=1, keepdim=True)[0])
+    mask_v, all_j = mask.max(dim=2)
+    b_ids, i_ids = torch.where(mask_v)
+    j_ids = all_j[b_ids, i_ids]
+    mconf = conf[b_ids, i_ids, j_ids]
+    scale = hw0_i[0] / h0
+    s0 = scale * scale0[b_ids] if scale0 is not None else scale
+    s1 = scale * scale1[b_ids] if scale1 is not None else scale
+    mk0 = torch.stack([i_ids % w0, torch.div(i_ids, w0, rounding_mode='trunc')], dim=1) * s0
+    mk1 = torch.stack([j_ids % w1, torch.div(j_ids, w1, rounding_mode='trunc')], dim=1) * s1
+    return {'b_ids': b_ids, 'i_ids': i_ids, 'j_ids': j_ids, 'mconf': mconf, 'mkpts0_c': mk0, 'mkpts1_c': mk1}
 
 
 def fine_windows(feat_f, b_ids, ids, stride, W):

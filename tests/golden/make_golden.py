@@ -183,7 +183,9 @@ def gen_widen(ref):
         m(f0, f1, data)
     st = data['stage_8c']
     save('widen_coarse_match', feat0=f0, feat1=f1, temperature=torch.tensor(0.1), next_conf01=st['next_conf_c01'], next_idx01=st['next_idx_c01'],
-         next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'])
+         next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'], hw=torch.tensor([h, w]), thr=torch.tensor(cfg['thr']),
+         border_rm=torch.tensor(cfg['border_rm']),
+         **{'m_' + k: st[k] for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0_c', 'mkpts1_c')})     # get_coarse_match (:91-153)
     # -- CascadeFinePreprocess
     fmod = importlib.import_module('src.model.functions.fine_matching')
     Bf, Cf, Cc, hc, wc, stride, M = 2, 32, 64, 10, 14, 2, 40
@@ -249,13 +251,17 @@ def gen_coarse_match_masked(ref):
     m0, m1 = band_mask([(10, 16), (12, 11)]), band_mask([(12, 13), (9, 16)])
     cfg = {'thr': 0.2, 'border_rm': 2, 'train_coarse_percent': 0.3, 'train_pad_num_gt_min': 200, 'match_type': 'dual_softmax',
            'dsmax_temperature': 0.1}
-    data = {'hw0_i': (h * 8, w * 8), 'hw1_i': (h * 8, w * 8), 'hw0_8c': (h, w), 'hw1_8c': (h, w), 'bs': B}
+    # mask_8c0 / mask_8c1 in `data` select the padded border removal of get_coarse_match (mask_border_with_padding, :124-127)
+    data = {'hw0_i': (h * 8, w * 8), 'hw1_i': (h * 8, w * 8), 'hw0_8c': (h, w), 'hw1_8c': (h, w), 'bs': B,
+            'mask_8c0': m0.reshape(B, h, w), 'mask_8c1': m1.reshape(B, h, w)}
     m = cmod.CoarseMatching(cfg).eval()
     with torch.no_grad():
         m(f0, f1, data, mask_c0=m0, mask_c1=m1)
     st = data['stage_8c']
     save('widen_coarse_match_masked', feat0=f0, feat1=f1, mask0=m0, mask1=m1, temperature=torch.tensor(0.1),
-         next_conf01=st['next_conf_c01'], next_idx01=st['next_idx_c01'], next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'])
+         next_conf01=st['next_conf_c01'], next_idx01=st['next_idx_c01'], next_conf10=st['next_conf_c10'], next_idx10=st['next_idx_c10'],
+         hw=torch.tensor([h, w]), thr=torch.tensor(cfg['thr']), border_rm=torch.tensor(cfg['border_rm']),
+         **{'m_' + k: st[k] for k in ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0_c', 'mkpts1_c')})
 
 
 def gen_relative_pe(ref):

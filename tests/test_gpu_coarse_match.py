@@ -45,7 +45,7 @@ def test_coarse_matching_module(dev):
     g = torch.Generator().manual_seed(5)
     f0 = torch.randn(1, 400, 256, generator=g)
     f1 = 0.8 * f0[:, torch.randperm(400, generator=g)] + 0.6 * torch.randn(1, 400, 256, generator=g)
-    data = {}
+    data = {'hw0_i': (160, 160), 'hw1_i': (160, 160), 'hw0_8c': (20, 20), 'hw1_8c': (20, 20)}
     casmtr_b200.CoarseMatching(cfg).eval()(f0.to(dev), f1.to(dev), data, level='8c')
     c01, i01, c10, i10, g01, g10 = _ref(f0, f1, 0.1)
     st = data['stage_8c']
@@ -97,10 +97,71 @@ def test_coarse_matching_module_with_masks(dev):
     g = load('widen_coarse_match_masked')
     cfg = {'thr': 0.2, 'border_rm': 2, 'match_type': 'dual_softmax', 'dsmax_temperature': float(g['temperature']), 'train_coarse_percent': 0.3,
            'train_pad_num_gt_min': 200}
-    data = {}
+    data = {'hw0_i': (96, 128), 'hw1_i': (96, 128), 'hw0_8c': (12, 16), 'hw1_8c': (12, 16)}
     mod = casmtr_b200.CoarseMatching(cfg).eval()
     mod(g['feat0'].to(dev), g['feat1'].to(dev), data, mask_c0=g['mask0'].bool().to(dev), mask_c1=g['mask1'].bool().to(dev))
     st = data['stage_8c']
     assert torch.equal(st['next_idx_c01'].cpu(), g['next_idx01']) and torch.equal(st['next_idx_c10'].cpu(), g['next_idx10'])
     with pytest.raises(RuntimeError):
         mod(g['feat0'].to(dev), g['feat1'].to(dev), data, mask_c0=g['mask0'].bool().to(dev))
+
+
+# ---- mutual-nearest-neighbour match list of the 1/8 stage (reference coarse_matching.py:91-153), second tensor-core pass
+@pytest.mark.parametrize('name,padded', [('widen_coarse_match', False), ('widen_coarse_match_masked', True)])
+def test_coarse_match_list_golden(dev, name, padded):
+    """Against the list the reference's own CoarseMatching.get_coarse_match produced (tests/golden/make_golden.py): ids bit-exact,
+    in torch.where order; mconf within 1e-5; keypoints exact.  The padded fixture carries mask_8c0 / mask_8c1 in `data`, i.e. the
+    padded border removal (mask_border_with_padding)."""
+    import casmtr_b200
+    from golden_util import load
+    g = load(name)
+    h, w = g['hw'].tolist()
+    cfg = {'thr': float(g['thr']), 'border_rm': int(g['border_rm']), 'match_type': 'dual_softmax', 'dsmax_temperature': float(g['temperature']),
+           'train_coarse_percent': 0.3, 'train_pad_num_gt_min': 200}
+    data = {'hw0_i': (h * 8, w * 8), 'hw1_i': (h * 8, w * 8), 'hw0_8c': (h, w), 'hw1_8c': (h, w)}
+    kw = {}
+    if padded:
+        m0, m1 = g['mask0'].bool().to(dev), g['mask1'].bool().to(dev)
+        data['mask_8c0'], data['mask_8c1'] = m0.reshape(-1, h, w), m1.reshape(-1, h, w)
+        kw = {'mask_c0': m0, 'mask_c1': m1}
+    casmtr_b200.CoarseMatching(cfg).eval()(g['feat0'].to(dev), g['feat1'].to(dev), data, **kw)
+    st = data['stage_8c']
+    assert st['b_ids'].numel() == g['m_b_ids'].numel() > 20
+    for k in ('b_ids', 'i_ids', 'j_ids'):
+        assert torch.equal(st[k].cpu(), g['m_' + k]), k
+    assert (st['mconf'].cpu() - g['m_mconf']).abs().max() < 1e-5
+    assert torch.equal(st['mkpts0_c'].cpu(), g['m_mkpts0_c'].float()) and torch.equal(st['mkpts1_c'].cpu(), g['m_mkpts1_c'].float())
+    assert torch.equal(st['m_bids'].cpu(), g['m_b_ids']) and not st['gt_mask'].any()
+
+
+@pytest.mark.parametrize('B,hw0,hw1,C,border', [(2, (40, 52), (40, 52), 256, 2), (1, (104, 104), (104, 104), 256, 0), (1, (30, 40), (24, 36), 64, 1)])
+def test_coarse_match_list_vs_oracle(dev, B, hw0, hw1, C, border):
+    """Larger random problems against the dense-matrix oracle (oracle/widen.py:coarse_matches); matches whose confidence sits within
+    1e-4 of the threshold, or whose row / column maximum of conf is not clear by 1e-4 relative, are excluded from the comparison."""
+    import casmtr_b200
+    from oracle import widen
+    L0, L1 = hw0[0] * hw0[1], hw1[0] * hw1[1]
+    g = torch.Generator().manual_seed(L0 + L1 + C)
+    f0 = torch.randn(B, L0, C, generator=g)
+    n = min(L0, L1)
+    f1 = torch.randn(B, L1, C, generator=g)
+    perm = torch.randperm(L1, generator=g)[:n]
+    f1[:, perm] = 0.8 * f0[:, :n] + 0.6 * f1[:, perm]          # planted correspondences
+    thr = 0.2
+    ref = widen.coarse_matches(f0, f1, 0.1, thr, border, hw0, hw1, (hw0[0] * 8, hw0[1] * 8))
+    cfg = {'thr': thr, 'border_rm': border, 'match_type': 'dual_softmax', 'dsmax_temperature': 0.1, 'train_coarse_percent': 0.3,
+           'train_pad_num_gt_min': 200}
+    data = {'hw0_i': (hw0[0] * 8, hw0[1] * 8), 'hw1_i': (hw1[0] * 8, hw1[1] * 8), 'hw0_8c': hw0, 'hw1_8c': hw1}
+    casmtr_b200.CoarseMatching(cfg).eval()(f0.to(dev), f1.to(dev), data)
+    st = data['stage_8c']
+    got = {(int(b), int(i)): (int(j), float(c)) for b, i, j, c in zip(st['b_ids'].cpu(), st['i_ids'].cpu(), st['j_ids'].cpu(), st['mconf'].cpu())}
+    want = {(int(b), int(i)): (int(j), float(c)) for b, i, j, c in zip(ref['b_ids'], ref['i_ids'], ref['j_ids'], ref['mconf'])}
+    assert len(want) > 100                                       # (at 10816 tokens the dual soft-max is thin: ~600 confident matches)
+    for key in set(got) | set(want):
+        c = (got.get(key) or want.get(key))[1]
+        if abs(c - thr) < 1e-4:
+            continue                                            # at the threshold: fp32 rounding decides
+        assert key in got and key in want, key
+        assert got[key][0] == want[key][0] and abs(got[key][1] - want[key][1]) < 1e-4, key
+    order = st['b_ids'].cpu() * L0 + st['i_ids'].cpu()
+    assert (order[1:] > order[:-1]).all()                       # torch.where order
