@@ -65,6 +65,9 @@ SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_cascade_qtatt_tokens_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_i64_p]
                                         + [C.c_int] * 9 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'casmtr_qtatt_guided_workspace_bytes': (C.c_size_t, [C.c_int] * 8),
+    'casmtr_qtatt_guided_fwd': (C.c_int, [c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, C.c_int, c_float_p] + [C.c_int] * 8
+                                + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'casmtr_set_pdl': (C.c_int, [C.c_int]),
     'casmtr_set_overlap': (C.c_int, [C.c_int]),
     'casmtr_window_idx_fwd': (C.c_int, [c_i64_p, c_i64_p] + [C.c_int] * 5 + [C.c_void_p]),

@@ -468,6 +468,60 @@ static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf,
     return CASMTR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ guided quadtree level
+static void carve_guided(Workspace &ws, int B, int C, int nhead, int h0, int w0, int h1, int w1, int K, float **q, float **k, float **v, int **idx, float **wsm) {
+    *q = ws.take<float>((size_t)B * h0 * w0 * C);
+    *k = ws.take<float>((size_t)B * h1 * w1 * C);
+    *v = ws.take<float>((size_t)B * h1 * w1 * C);
+    *idx = ws.take<int>((size_t)B * (h0 / 2) * (w0 / 2) * nhead * K);
+    *wsm = ws.take<float>(CASMTR_MAX_LEVELS);
+}
+
+size_t casmtr_qtatt_guided_workspace_bytes(int B, int C, int nhead, int h0, int w0, int h1, int w1, int K) {
+    if (B <= 0 || C <= 0 || nhead <= 0 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0 || K <= 0) return 0;
+    Workspace ws(nullptr, 0);
+    float *q, *k, *v, *wsm;
+    int *idx;
+    carve_guided(ws, B, C, nhead, h0, w0, h1, w1, K, &q, &k, &v, &idx, &wsm);
+    return ws.off;
+}
+
+int casmtr_qtatt_guided_fwd(const float *query, const float *key, const float *value, const int64_t *topk_pos,
+                            const float *level_weight, int weight_len, float *out,
+                            int B, int nhead, int D, int h0, int w0, int h1, int w1, int K,
+                            void *workspace, size_t workspace_bytes, casmtr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CASMTR_REQUIRE(D == 32, CASMTR_E_UNSUPPORTED, "qtatt_guided: head dim %d unsupported (D == 32)", D);
+    CASMTR_REQUIRE(B >= 1 && nhead >= 1 && h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0, CASMTR_E_INVALID, "qtatt_guided: bad sizes");
+    CASMTR_REQUIRE(h0 % 2 == 0 && w0 % 2 == 0 && h1 % 2 == 0 && w1 % 2 == 0, CASMTR_E_INVALID, "qtatt_guided: grids %dx%d / %dx%d must be even", h0, w0, h1, w1);
+    CASMTR_REQUIRE(K >= 1 && K <= 32, CASMTR_E_UNSUPPORTED, "qtatt_guided: K=%d must be in [1,32]", K);
+    CASMTR_REQUIRE(weight_len >= 1 && weight_len <= CASMTR_MAX_LEVELS, CASMTR_E_INVALID, "qtatt_guided: weight_len=%d must be in [1,%d]", weight_len, CASMTR_MAX_LEVELS);
+    CASMTR_REQUIRE(query && key && value && topk_pos && level_weight && out && workspace, CASMTR_E_INVALID, "qtatt_guided: null pointer");
+    const int C = nhead * D;
+    Workspace ws(workspace, workspace_bytes);
+    float *qt, *kt, *vt, *wsm;
+    int *idx;
+    carve_guided(ws, B, C, nhead, h0, w0, h1, w1, K, &qt, &kt, &vt, &idx, &wsm);
+    CASMTR_REQUIRE(ws.ok(), CASMTR_E_WORKSPACE, "qtatt_guided: workspace %zu < %zu bytes", workspace_bytes, ws.off);
+    TransposeJobs jobs;
+    jobs.n = 3;
+    jobs.job[0] = TransposeJob{query, qt, C, h0 * w0, 0};
+    jobs.job[1] = TransposeJob{key, kt, C, h1 * w1, 0};
+    jobs.job[2] = TransposeJob{value, vt, C, h1 * w1, 0};
+    int rc = launch_transpose_jobs(jobs, B, stream);
+    if (rc != CASMTR_OK) return rc;
+    rc = launch_guided_prep(topk_pos, idx, (size_t)B * (h0 / 2) * (w0 / 2), K, nhead, h1 / 2, w1 / 2, level_weight, weight_len, wsm, stream);
+    if (rc != CASMTR_OK) return rc;
+    FineParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.q = qt; fp.k = kt; fp.v = vt;
+    fp.prev_idx = idx; fp.out = out;
+    fp.wsm = wsm; fp.level = 0;
+    fp.B = B; fp.nh = nhead; fp.h0 = h0; fp.w0 = w0; fp.h1 = h1; fp.w1 = w1; fp.w_prev = w1 / 2;
+    fp.kp = K; fp.topk = 0; fp.dil = 1; fp.final_level = 1;
+    return launch_quad_attention(fp, stream);
+}
+
 // ------------------------------------------------------------------------------------------------ cascade attention
 size_t casmtr_cascade_qtatt_workspace_bytes(int B, int C, int h0, int w0, int h1, int w1) {
     if (B <= 0 || C <= 0 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0) return 0;

@@ -26,6 +26,8 @@ struct PoolJobs {
 };
 int launch_pool_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream);
 int launch_pool2_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream);
+int launch_guided_prep(const int64_t *pos, int *idx, size_t n_cells, int K, int nh, int hv, int wv, const float *weight, int n_w, float *wsm,
+                       cudaStream_t stream);
 int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
                        size_t n_tok, int nh, int k, cudaStream_t stream);
 

@@ -256,6 +256,37 @@ __global__ void topk_to_api_kernel(const int *__restrict__ idx, const float *__r
     }
 }
 
+// QTAttGuided: topk_pos [2, B, Np, K, nh] int64 (row, col on the hv x wv grid) -> the level kernels' candidate lists [B, Np, nh, K]
+// int32 (flat cell index), and wsm[0..n) = softmax(level_weight[0..n))
+__global__ void guided_prep_kernel(const int64_t *__restrict__ pos, int *__restrict__ idx, size_t n_cells, int K, int nh, int hv, int wv,
+                                   const float *__restrict__ weight, int n_w, float *__restrict__ wsm) {
+    pdl_sync();
+    const size_t total = n_cells * K * nh;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(o % nh);
+        const int k = (int)((o / nh) % K);
+        const size_t cell = o / ((size_t)nh * K);
+        const int r = (int)min(max(pos[o], (int64_t)0), (int64_t)hv - 1), c = (int)min(max(pos[total + o], (int64_t)0), (int64_t)wv - 1);
+        idx[(cell * nh + h) * K + k] = r * wv + c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && wsm) {
+        float mx = -INFINITY, den = 0.f;
+        for (int l = 0; l < n_w; ++l) mx = fmaxf(mx, weight[l]);
+        for (int l = 0; l < n_w; ++l) den += expf(weight[l] - mx);
+        for (int l = 0; l < n_w && l < CASMTR_MAX_LEVELS; ++l) wsm[l] = expf(weight[l] - mx) / den;
+    }
+}
+
+int launch_guided_prep(const int64_t *pos, int *idx, size_t n_cells, int K, int nh, int hv, int wv, const float *weight, int n_w, float *wsm,
+                       cudaStream_t stream) {
+    const size_t total = n_cells * K * nh;
+    if (total == 0) return CASMTR_OK;
+    LaunchScope ls(CASMTR_K_LAYOUT, stream);
+    launch_k(guided_prep_kernel, (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, stream, pos, idx, n_cells, K, nh, hv, wv, weight, n_w, wsm);
+    CASMTR_CHECK_LAUNCH("guided_prep_kernel");
+    return CASMTR_OK;
+}
+
 int launch_topk_to_api(const int *idx, const float *score, int64_t *idx_out, float *score_out,
                        size_t n_tok, int nh, int k, cudaStream_t stream) {
     const size_t total = n_tok * nh;            // one warp each

@@ -269,6 +269,30 @@ def qtatt_tokens_forward(q0, k0, v0, hw_q, hw_k, topks, nhead, weight=None, attn
     return out
 
 
+def qtatt_guided_forward(query, key, value, topk_pos, weight, nhead):
+    """One guided quadtree level (QTAttGuided, single-level pyramid): query [B,C,h0,w0], key / value [B,C,h1,w1], topk_pos
+    [2,B,(h0/2)*(w0/2),K,nhead] int64 (row, col of the K key cells per query cell and head on the (h1/2 x w1/2) grid), weight = the
+    module's raw level weights.  -> message [B, h0*w0, nhead, D] in raster order, scaled by softmax(weight)[0]."""
+    _chk(query, 'query', torch.float32), _chk(key, 'key', torch.float32), _chk(value, 'value', torch.float32)
+    _chk(topk_pos, 'topk_pos', torch.int64)
+    B, Cc, h0, w0 = query.shape
+    h1, w1 = key.shape[2:]
+    if topk_pos.dim() != 5 or topk_pos.shape[:3] != (2, B, (h0 // 2) * (w0 // 2)) or topk_pos.shape[4] != nhead:
+        raise RuntimeError(f'topk_pos must be [2,B,(h0/2)*(w0/2),K,nhead], got {tuple(topk_pos.shape)}')
+    K = topk_pos.shape[3]
+    weight = _chk(weight.detach().to(torch.float32).contiguous(), 'weight', torch.float32)
+    dev = query.device
+    out = torch.empty(B, h0 * w0, nhead, Cc // nhead, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib().casmtr_qtatt_guided_workspace_bytes(B, Cc, nhead, h0, w0, h1, w1, K)
+        if nbytes == 0:
+            check(-1, 'casmtr_qtatt_guided_workspace_bytes')
+        ws = _workspace(nbytes, dev)
+        check(lib().casmtr_qtatt_guided_fwd(_ptr(query), _ptr(key), _ptr(value), _ptr(topk_pos), _ptr(weight), weight.numel(), _ptr(out),
+                                            B, nhead, Cc // nhead, h0, w0, h1, w1, K, _ptr(ws), ws.numel(), _stream(out)), 'casmtr_qtatt_guided_fwd')
+    return out
+
+
 def window_warp_idx(next_idx, H, W, window=5):
     """next_idx [B,L] int64 on an H x W grid -> [B,L,window^2,2] (row, col) of the border-shifted window around each match
     (CascadeFeatureTransformer.get_window_warp_idx, reference transformer.py:416-440)."""

@@ -71,8 +71,13 @@ class QuadtreeAttention(nn.Module):
         H1 = H if H1 is None else H1
         W1 = W if W1 is None else W1
         B, N, C = x.shape
-        if self.attn_type == 'Guided':
-            raise NotImplementedError('QTAttGuided is used by no shipped config and is not built (SURVEY.md section 8 a6)')
+        if self.attn_type == 'Guided':        # scale 1 only (see QTAttGuided): NCHW maps, as the guided module consumes them
+            if self.scale != 1:
+                raise NotImplementedError("QTAttGuided: the reference's merge only runs on a single-level pyramid (scale = 1)")
+            q, k, v = (_project(c, t) for c, t in ((self.q_proj, x), (self.k_proj, target), (self.v_proj, target)))
+            nchw = lambda t, h, w: t.transpose(1, 2).reshape(B, C, h, w).contiguous()
+            msg = self.py_att([nchw(q, H, W)], [nchw(k, H1, W1)], [nchw(v, H1, W1)], rel_pos=rel_pos, topk_pos=topk_pos).reshape(B, -1, C)
+            return self.proj_drop(self.proj(msg))
         if rel_pos is not None:
             raise NotImplementedError('QTAttB rel_pos is not implemented by casmtr_b200')
         if getattr(self.py_att, 'lepe', False):

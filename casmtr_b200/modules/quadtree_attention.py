@@ -69,9 +69,14 @@ class QTAttB(nn.Module):
 
 
 class QTAttGuided(nn.Module):
-    """reference :289-389.  Only reachable with SELF_ATTN_TYPE='topk', which no shipped config selects
-    (SURVEY.md §8 a6); the class keeps the constructor and the ``weight`` state-dict key so reference
-    checkpoints load, the forward is not implemented on the B200 path."""
+    """reference :289-389.  Quadtree levels seeded by an external `topk_pos` instead of a dense coarsest level; reachable with
+    SELF_ATTN_TYPE='topk' (src/model/modules/quadtree_attention.py:37), which no shipped config selects.
+
+    The reference's merge loop reshapes every level with `queries[-i]` (:385): for i = 0 that is `queries[0]`, the FINEST map's
+    height, where half of the current level's height is meant.  With more than one level the shapes no longer fit and the reference
+    itself raises; with ONE level it runs, but the wrong height permutes the tokens.  This drop-in supports exactly what the
+    reference can run -- a single-level pyramid -- and reproduces its output INCLUDING that permutation (`reference_order=True`, the
+    default); `reference_order=False` returns the tokens in raster order, which is what the merge was written to produce."""
 
     def __init__(self, nhead, dim, scale, topks=[32], use_dropout=False):
         super().__init__()
@@ -80,9 +85,43 @@ class QTAttGuided(nn.Module):
         self.nhead = nhead
         self.dim = dim
         self.register_parameter('weight', nn.Parameter(torch.randn(scale)))
+        self.reference_order = True
+        self._perm = {}
+
+    def _reference_permutation(self, h0, w0, device):
+        """dst -> src token map of the reference's rearrange 'b (H W) (t1 t2) h d -> b (H t1 W t2) h d' with H = h0 (:385) applied to
+        per-cell messages, relative to the raster order of the (h0 x w0) query grid."""
+        key = (h0, w0, str(device))
+        if key not in self._perm:
+            Np = (h0 // 2) * (w0 // 2)
+            if Np % h0:
+                raise RuntimeError(f"QTAttGuided: the reference's merge cannot reshape {Np} cells with H={h0} (quadtree_attention.py:385)")
+            W = Np // h0
+            p = torch.arange(Np)
+            t = torch.arange(4)
+            y, x = p // (w0 // 2), p % (w0 // 2)
+            src = ((2 * y[:, None] + t[None] // 2) * w0 + 2 * x[:, None] + t[None] % 2)                     # raster token of (cell, child)
+            dst = (((p // W)[:, None] * 2 + t[None] // 2) * W + (p % W)[:, None]) * 2 + t[None] % 2           # where the reference puts it
+            perm = torch.empty(h0 * w0, dtype=torch.int64)
+            perm[dst.reshape(-1)] = src.reshape(-1)
+            self._perm[key] = perm.to(device)
+        return self._perm[key]
 
     def forward(self, queries, keys, values, q_mask=None, kv_mask=None, rel_pos=None, topk_pos=None):
-        raise NotImplementedError('QTAttGuided.forward is not implemented by casmtr_b200 (unused by every shipped config)')
+        """queries / keys / values: one-level lists of [N,C,H,W]; topk_pos [2,N,(H/2*W/2),K,nhead] (row, col of the key cells at half
+        the key resolution) -> message [N, H*W, nhead, dim]."""
+        if len(queries) != 1:
+            raise NotImplementedError("QTAttGuided: the reference's merge (quadtree_attention.py:372-385) only runs on a single-level "
+                                      'pyramid; multi-level guided attention is not defined by it')
+        if rel_pos is not None:
+            raise NotImplementedError('QTAttGuided rel_pos is not implemented by casmtr_b200')
+        if topk_pos is None:
+            raise RuntimeError('QTAttGuided needs topk_pos')
+        q = _f32c(queries[0])
+        out = F.qtatt_guided_forward(q, _f32c(keys[0]), _f32c(values[0]), topk_pos.to(torch.int64).contiguous(), self.weight, self.nhead)
+        if self.reference_order:
+            out = out.index_select(1, self._reference_permutation(q.shape[2], q.shape[3], out.device))
+        return out
 
 
 class CascadeQTAttB(nn.Module):

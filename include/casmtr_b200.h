@@ -179,6 +179,21 @@ CASMTR_API int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *desc, const floa
                      int64_t *const *topk_idx_out, float *const *topk_score_out,
                      void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
 
+/* One guided quadtree level (QTAttGuided.process_fine_level + merge, reference quadtree_attention.py:298-389; reachable through
+ * SELF_ATTN_TYPE = 'topk'): the 4 children of every query cell attend to the 4 children of each of K externally supplied key cells.
+ *   query [B,C,h0,w0], key / value [B,C,h1,w1] NCHW fp32; topk_pos [2,B,(h0/2)*(w0/2),K,nhead] int64 = (row, col) of the key cells on
+ *   the (h1/2 x w1/2) grid, per head (clamped into the grid; the reference reads out of bounds otherwise);
+ *   level_weight device [weight_len] = the module's raw `weight`: the message is scaled by softmax(weight)[0] (:375-380);
+ *   out [B, h0*w0, nhead, D] in RASTER order of the query grid.
+ * The reference's own merge (:385) reshapes with queries[-0] = the only level's height instead of half of it, which permutes the
+ * tokens; the Python module applies that permutation on top of this entry point's raster output to stay a drop-in.
+ * K <= 32, D == 32.  Workspace: casmtr_qtatt_guided_workspace_bytes. */
+CASMTR_API size_t casmtr_qtatt_guided_workspace_bytes(int B, int C, int nhead, int h0, int w0, int h1, int w1, int K);
+CASMTR_API int casmtr_qtatt_guided_fwd(const float *query, const float *key, const float *value, const int64_t *topk_pos,
+                            const float *level_weight, int weight_len, float *out,
+                            int B, int nhead, int D, int h0, int w0, int h1, int w1, int K,
+                            void *workspace, size_t workspace_bytes, casmtr_stream_t stream);
+
 /* Launch options.  Both are settings of the CALLING THREAD (thread-local, default on), not of the process: a second host thread
  * is unaffected, and a stream capture records what the capturing thread selected.  Per-call options live in the descriptors
  * (casmtr_qtatt_desc.flags / .concurrent_calls).

@@ -221,3 +221,31 @@ def cascade_qtatt_b(query, key, value, topk_pos, rel_pos, nhead, dilated=1):
     message = m.permute(0, 2, 1, 3).reshape(B, h0 * w0, C).contiguous()
     up = quad_to_raster(cand.reshape(B, 1, hp * wp, 1, K).expand(B, 1, hp * wp, 4, K), hp, wp)
     return message, up.reshape(B, h0 * w0, K).contiguous()
+
+
+# ----------------------------------------------------------------------------- QTAttGuided (single level)
+def qtatt_guided(query, key, value, topk_pos, weight, nhead, reference_order=True):
+    """QTAttGuided.forward on a ONE-level pyramid (qta.py:289-389; the only case the reference's merge can run, see :385).
+    query [B,C,h0,w0], key / value [B,C,h1,w1], topk_pos [2,B,(h0/2*w0/2),K,nh] (row, col at half the key resolution), weight
+    [scale].  :311-318 candidates = the 2x2 children of every key cell, order k*4+f; :325-327 scaled logits; :335 softmax over the 4K
+    candidates; :342 message = A.V; :375-380 message * softmax(weight)[0]; :385 the rearrange with H = queries[-0].shape[2] = h0
+    (reference_order=True reproduces it; False gives the raster order of the query grid).  Returns [B, h0*w0, nh, D]."""
+    B, C, h0, w0 = query.shape
+    h1, w1 = key.shape[2:]
+    D = C // nhead
+    hp, wp = h0 // 2, w0 // 2
+    Np = hp * wp
+    r2, c2 = topk_pos[0] * 2, topk_pos[1] * 2                                   # [B,Np,K,nh]
+    cand = torch.stack([(r2 + x) * w1 + c2 + y for x in (0, 1) for y in (0, 1)], dim=3)          # [B,Np,K,4,nh]
+    K4 = cand.shape[2] * 4
+    cand = cand.reshape(B, Np, K4, nhead).permute(0, 3, 1, 2)                    # [B,nh,Np,4K]
+    kt, vt = tokens(key, nhead), tokens(value, nhead)
+    qc = children(query, nhead)                                                 # [B,nh,Np,4,D]
+    kc, vc = gather_rows(kt, cand), gather_rows(vt, cand)
+    A = torch.softmax(torch.matmul(qc, kc.transpose(-1, -2)) * (1.0 / D ** 0.5), dim=-1)
+    m = torch.matmul(A, vc) * torch.softmax(weight, dim=0)[0]                   # [B,nh,Np,4,D]
+    m = m.permute(0, 2, 3, 1, 4)                                                # [B,Np,4,nh,D]
+    H = h0 if reference_order else hp
+    W = Np // H
+    out = m.reshape(B, H, W, 2, 2, nhead, D).permute(0, 1, 3, 2, 4, 5, 6)       # b (H t1 W t2) h d
+    return out.reshape(B, h0 * w0, nhead, D).contiguous()

@@ -101,7 +101,7 @@ def load():
     cf = importlib.import_module('src.model.functions.cascade_functions')
     cm = importlib.import_module('src.model.functions.cascade_matching')
     fm = importlib.import_module('src.model.functions.fine_matching')
-    ns.QTAttA, ns.QTAttB, ns.CascadeQTAttB = qta.QTAttA, qta.QTAttB, qta.CascadeQTAttB
+    ns.QTAttA, ns.QTAttB, ns.CascadeQTAttB, ns.QTAttGuided = qta.QTAttA, qta.QTAttB, qta.CascadeQTAttB, qta.QTAttGuided
     ns.SmartQTAttB, ns.torch_gather_b2 = smart.QTAttB, smart.torch_gather_b2
     ns.torch_gather = cf.torch_gather
     ns.CascadeMatching = cm.CascadeMatching

@@ -325,6 +325,24 @@ def gen_relative_pe(ref):
     save('widen_relative_pe', hw8=torch.tensor(hw8), nhead=torch.tensor(nh), **out)
 
 
+def gen_guided(ref):
+    """The reference's QTAttGuided on a single-level pyramid (the only case its merge can run, quadtree_attention.py:385)."""
+    g = torch.Generator().manual_seed(41)
+    B, nh, C, h, w, K = 2, 4, 128, 16, 24, 8
+    q, k, v = (torch.randn(B, C, h, w, generator=g) for _ in range(3))
+    pos = torch.stack([torch.randint(0, h // 2, (B, (h // 2) * (w // 2), K, nh), generator=g),
+                       torch.randint(0, w // 2, (B, (h // 2) * (w // 2), K, nh), generator=g)])
+    m = ref.QTAttGuided(nh, C // nh, scale=1, topks=[K]).eval()
+    with torch.no_grad():
+        m.weight.copy_(torch.tensor([0.7]))
+        out = m([q], [k], [v], topk_pos=pos)
+    m3 = ref.QTAttGuided(nh, C // nh, scale=3, topks=[K]).eval()                 # the weight vector may be longer than the pyramid
+    with torch.no_grad():
+        m3.weight.copy_(torch.tensor([0.7, -0.4, 1.3]))
+        out3 = m3([q], [k], [v], topk_pos=pos)
+    save('qtatt_guided', q=q, k=k, v=v, topk_pos=pos, nhead=torch.tensor(nh), out=out, weight3=m3.weight.detach(), out3=out3)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -337,3 +355,4 @@ if __name__ == '__main__':
     gen_widen(ref)
     gen_coarse_match_masked(ref)
     gen_relative_pe(ref)
+    gen_guided(ref)

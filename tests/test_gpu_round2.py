@@ -197,3 +197,52 @@ def test_second_device_in_the_same_process():
         outs.append((a.cpu(), m.cpu(), o['next_idx01'].cpu()))
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+def test_qtatt_guided_single_level(dev):
+    """QTAttGuided: drop-in for the one case the reference can run (single-level pyramid), against the reference's own
+    output (tests/golden/qtatt_guided.npz) and, in raster order, against the oracle; the layer one level up (QuadtreeAttention with
+    attn_type='Guided', scale=1) against the oracle's layer restatement."""
+    from golden_util import load
+    from casmtr_b200 import QTAttGuided, QuadtreeAttention
+    g = load('qtatt_guided')
+    nh = int(g['nhead'])
+    pos = g['topk_pos'].long()
+    q, k, v = g['q'].to(dev), g['k'].to(dev), g['v'].to(dev)
+    m = QTAttGuided(nh, q.shape[1] // nh, scale=1, topks=[pos.shape[3]]).to(dev).eval()
+    with torch.no_grad():
+        m.weight.copy_(torch.tensor([0.7]))
+        out = m([q], [k], [v], topk_pos=pos.to(dev))
+    assert (out.cpu() - g['out']).abs().max() < 1e-4
+    m3 = QTAttGuided(nh, q.shape[1] // nh, scale=3, topks=[pos.shape[3]]).to(dev).eval()
+    with torch.no_grad():
+        m3.weight.copy_(g['weight3'])
+        assert (m3([q], [k], [v], topk_pos=pos.to(dev)).cpu() - g['out3']).abs().max() < 1e-4
+        m3.reference_order = False
+        ras = m3([q], [k], [v], topk_pos=pos.to(dev))
+    assert (ras.cpu() - oqt.qtatt_guided(g['q'], g['k'], g['v'], pos, g['weight3'], nh, reference_order=False)).abs().max() < 1e-4
+    with pytest.raises(NotImplementedError):
+        m([q, q], [k, k], [v, v], topk_pos=pos.to(dev))
+    # other K / head counts, rectangular, keys on a different grid than the queries
+    gen = torch.Generator().manual_seed(3)
+    for (B, nh2, h0, w0, h1, w1, K) in ((1, 8, 32, 40, 32, 40, 32), (2, 2, 8, 16, 12, 20, 5), (1, 4, 16, 16, 24, 8, 16)):
+        C = nh2 * 32
+        q2, k2, v2 = torch.randn(B, C, h0, w0, generator=gen), torch.randn(B, C, h1, w1, generator=gen), torch.randn(B, C, h1, w1, generator=gen)
+        Np = (h0 // 2) * (w0 // 2)
+        p2 = torch.stack([torch.randint(0, h1 // 2, (B, Np, K, nh2), generator=gen), torch.randint(0, w1 // 2, (B, Np, K, nh2), generator=gen)])
+        wt = torch.randn(2, generator=gen)
+        ref = oqt.qtatt_guided(q2, k2, v2, p2, wt, nh2, reference_order=False)
+        got = F.qtatt_guided_forward(q2.to(dev), k2.to(dev), v2.to(dev), p2.to(dev), wt.to(dev), nh2)
+        assert (got.cpu() - ref).abs().max() < 1e-4, (B, nh2, h0, w0, K)
+    # the attention layer around it
+    layer = QuadtreeAttention(128, nh, [pos.shape[3]], scale=1, attn_type='Guided').to(dev).eval()
+    x = torch.randn(2, 16 * 24, 128, generator=gen).to(dev)
+    with torch.no_grad():
+        y = layer(x, x, 16, 24, topk_pos=pos.to(dev))
+        sd = {n: t.cpu() for n, t in layer.state_dict().items()}
+        xq = torch.nn.functional.conv2d(x.cpu().transpose(1, 2).reshape(2, 128, 16, 24), sd['q_proj.weight'])
+        xk = torch.nn.functional.conv2d(x.cpu().transpose(1, 2).reshape(2, 128, 16, 24), sd['k_proj.weight'])
+        xv = torch.nn.functional.conv2d(x.cpu().transpose(1, 2).reshape(2, 128, 16, 24), sd['v_proj.weight'])
+        msg = oqt.qtatt_guided(xq, xk, xv, pos, sd['py_att.weight'], nh).reshape(2, -1, 128)
+        want = torch.nn.functional.linear(msg, sd['proj.weight'], sd['proj.bias'])
+    assert (y.cpu() - want).abs().max() < 1e-3
