@@ -546,18 +546,16 @@ def pack_matches(m, pair_offset, cap):
     on the device: no host synchronisation."""
     count = m.get('count')
     M = int(m['b_ids'].shape[0])
-    if count is not None:
-        cap = min(cap, M)
-    elif M > cap:
+    if count is None and M > cap:
         raise RuntimeError(f'pack_matches: {M} matches exceed the static capacity {cap}')
     dev = m['b_ids'].device
-    out = torch.empty(cap + 1, 44, dtype=torch.uint8, device=dev)
+    out = torch.empty(cap + 1, 44, dtype=torch.uint8, device=dev)      # always cap + 1 rows: every rank's block has the same size
     t = [_chk(m[k].contiguous(), k, dt) for k, dt in (('b_ids', torch.int64), ('i_ids', torch.int64), ('j_ids', torch.int64),
                                                       ('mconf', torch.float32), ('mkpts0', torch.float32), ('mkpts1', torch.float32))]
     with torch.cuda.device(dev):
         if count is not None:
             _chk(count, 'count', torch.int32)
-            check(lib().casmtr_pack_matches_dev(*[_ptr(x) for x in t], _ptr(count), int(pair_offset), int(cap), _ptr(out), _stream(out)),
+            check(lib().casmtr_pack_matches_dev(*[_ptr(x) for x in t], _ptr(count), int(pair_offset), int(min(cap, M)), _ptr(out), _stream(out)),
                   'casmtr_pack_matches_dev')
         else:
             check(lib().casmtr_pack_matches(*[_ptr(x) for x in t], M, int(pair_offset), int(cap), _ptr(out), _stream(out)),

@@ -43,7 +43,7 @@ ncu)
   BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-gpu-baselines --no-graph --no-sweep --no-next-rows ${NCU_BENCH_ARGS}"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-gpu-baselines --no-graph --no-sweep --no-next-rows ${NCU_BENCH_ARGS} > $OUT/${TAG}_ncu_launch.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pool2_tokens|qtatt_coarse|quad_cta|quad_attention_kernel' -c 4 -f -o $OUT/${TAG}_qtatt $BENCH > $OUT/${TAG}_ncu_a.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pool2_tokens|coarse_prep|qtatt_coarse|quad_cta|quad_attention_kernel' -c 5 -f -o $OUT/${TAG}_qtatt $BENCH > $OUT/${TAG}_ncu_a.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'cascade_att_tile|quad_attention_list|cascade_match|extract_|fine_match' -c 7 -f -o $OUT/${TAG}_cascade $BENCH > $OUT/${TAG}_ncu_b.log 2>&1
   for r in qtatt cascade; do
     ncu -i $OUT/${TAG}_$r.ncu-rep --page raw --csv > $OUT/${TAG}_${r}_raw.csv 2>/dev/null

@@ -19,7 +19,7 @@ TAG = sys.argv[1]
 OUT, PROF = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 KIND = [('transpose_vec', 'layout'), ('qtatt_coarse', 'qt_coarse'), ('quad_cta', 'qt_fine_mid'), ('quad_attention_kernel', 'qt_fine_last'),
         ('cascade_att_tile', 'cascade_att'), ('quad_attention_list', 'cascade_fallback'), ('cascade_match_tile', 'cascade_match'),
-        ('cascade_match_cell', 'cascade_match_fallback'), ('coarse_rowstats', 'coarse_match'), ('pool2_tokens', 'pool_tokens'),
+        ('cascade_match_cell', 'cascade_match_fallback'), ('coarse_rowstats', 'coarse_match'), ('pool2_tokens', 'layout'), ('coarse_prep', 'coarse_prep'),
         ('fine_window_gather', 'fine_window_gather'), ('fine_match', 'fine_match'), ('extract_mask', 'extract'),
         ('relative_pe_kernel', 'relative_pe'), ('score5d_bwd', 'score5d_bwd'), ('value_agg_bwd', 'value_agg_bwd'), ('score3d_bwd', 'score3d_bwd')]
 

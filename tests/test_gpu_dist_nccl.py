@@ -15,6 +15,14 @@ KEYS = ('b_ids', 'i_ids', 'j_ids', 'mconf', 'mkpts0', 'mkpts1')
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:      # noqa: BLE001  (the parent must hear about it instead of waiting for a rank that will never answer)
+        import traceback
+        q.put((rank, 'error', traceback.format_exc()[-2000:], None))
+
+
+def _worker_body(rank, world, port, q):
     import torch.distributed as dist
     from casmtr_b200 import dist as cdist
     from casmtr_b200 import pipeline
@@ -56,10 +64,16 @@ def test_gathered_match_list_equals_the_single_rank_lists():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=240) for _ in range(2)]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()                                    # the exact processes this test started
+    for r in res:
+        assert r[1] != 'error', r[2]
+    res = sorted(res, key=lambda t: t[0])
     (_, m0, a0, b0), (_, m1, a1, b1) = res
     assert len(m0['b_ids']) > 10 and len(m1['b_ids']) > 10
     want = {k: m0[k] + m1[k] for k in KEYS}
