@@ -320,7 +320,8 @@ size_t casmtr_qtatt_workspace_bytes(const casmtr_qtatt_desc *desc) {
 
 // the levels themselves, on token-major pyramids bf.q/k/v
 static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join = nullptr);
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join = nullptr,
+                        bool tc_prepped = false);
 
 int casmtr_qtatt_fwd(const casmtr_qtatt_desc *d,
                      const float *const *queries, const float *const *keys, const float *const *values,
@@ -398,32 +399,42 @@ int casmtr_qtatt_tokens_fwd(const casmtr_qtatt_desc *d, const float *q0, const f
     const int C = d->nhead * d->D;
     bf.q[0] = const_cast<float *>(q0); bf.k[0] = const_cast<float *>(k0); bf.v[0] = const_cast<float *>(v0);   // read in place
     ConcurrencyScope cc(d->concurrent_calls);
+    bool tc_prepped = false;
     for (int l = 1; l < d->levels; ++l) {
         PoolJobs pj;
         pj.n = 3;
-        const bool two = l + 1 < d->levels && d->qh[l - 1] % 4 == 0 && d->qw[l - 1] % 4 == 0 && d->kh[l - 1] % 4 == 0 && d->kw[l - 1] % 4 == 0;
+        const bool two = l + 1 < d->levels && C % 32 == 0 && d->qh[l - 1] % 4 == 0 && d->qw[l - 1] % 4 == 0 && d->kh[l - 1] % 4 == 0 && d->kw[l - 1] % 4 == 0;
         pj.job[0] = PoolJob{bf.q[l - 1], bf.q[l], d->qh[l - 1], d->qw[l - 1], two ? bf.q[l + 1] : nullptr};
         pj.job[1] = PoolJob{bf.k[l - 1], bf.k[l], d->kh[l - 1], d->kw[l - 1], two ? bf.k[l + 1] : nullptr};
         pj.job[2] = PoolJob{bf.v[l - 1], bf.v[l], d->kh[l - 1], d->kw[l - 1], two ? bf.v[l + 1] : nullptr};
+        if (two && l + 1 == d->levels - 1 && bf.tc_ws) {
+            // the pass that produces the coarsest maps also leaves the tensor-core level's split operands next to them
+            const int lc = d->levels - 1;
+            const CoarseTcOperands op = coarse_tc_operands(bf.tc_ws, d->B, d->qh[lc] * d->qw[lc], d->kh[lc] * d->kw[lc], C);
+            pj.job[0].lo2 = op.q_lo;
+            pj.job[1].lo2 = op.k_lo;
+            pj.job[2].vt_hi = op.vt_hi; pj.job[2].vt_lo = op.vt_lo; pj.job[2].Sp = op.Sp;
+            tc_prepped = true;
+        }
         rc = two ? launch_pool2_tokens(pj, d->B, C, stream) : launch_pool_tokens(pj, d->B, C, stream);
         if (rc != CASMTR_OK) return rc;
         if (two) ++l;
     }
-    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream);
+    return qtatt_levels(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream, nullptr, tc_prepped);
 }
 
 static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join);
+                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join, bool tc_prepped);
 
 static int qtatt_levels(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join) {
-    const int rc = qtatt_levels_impl(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream, join);
+                        int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t join, bool tc_prepped) {
+    const int rc = qtatt_levels_impl(d, bf, level_weight, out, topk_idx_out, topk_score_out, stream, join, tc_prepped);
     if (join) cudaStreamWaitEvent(stream, join, 0);     // an early error return must not leave the side lane un-joined
     return rc;
 }
 
 static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf, const float *level_weight, float *out,
-                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join) {
+                             int64_t *const *topk_idx_out, float *const *topk_score_out, cudaStream_t stream, cudaEvent_t &join, bool tc_prepped) {
     int rc = CASMTR_OK;
     const float *wts = d->type == 0 ? level_weight : nullptr;
     for (int i = 0; i < d->levels; ++i) {
@@ -440,7 +451,7 @@ static int qtatt_levels_impl(const casmtr_qtatt_desc *d, const QtattBuffers &bf,
             cp.acc = dst; cp.topk_idx = bf.tk_idx[0]; cp.topk_score = bf.tk_sc[0];
             cp.level_weight = wts; cp.levels = d->levels; cp.n_weights = d->weight_len > 0 ? d->weight_len : d->levels; cp.wsm = wts ? bf.wsm : nullptr;
             cp.B = d->B; cp.Sq = d->qh[l] * d->qw[l]; cp.Sk = d->kh[l] * d->kw[l];
-            cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type; cp.tc_ws = bf.tc_ws;
+            cp.nh = d->nhead; cp.topk = d->topks[0]; cp.type_a = d->type; cp.tc_ws = bf.tc_ws; cp.tc_prepped = tc_prepped;
             rc = launch_qtatt_coarse(cp, stream);
         } else {
             FineParams fp;

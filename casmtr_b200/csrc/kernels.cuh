@@ -19,6 +19,10 @@ struct PoolJob {
     float *dst;         // [B, (h/2)*(w/2), C]
     int h, w;
     float *dst2;        // launch_pool2_tokens only: [B, (h/4)*(w/4), C]
+    // launch_pool2_tokens only, optional operands of the tensor-core coarsest level derived from dst2 (qtatt_coarse_tc.cu):
+    float *lo2;                     // x - trunc_tf32(x), same layout as dst2
+    unsigned short *vt_hi, *vt_lo;  // dst2 * 2^8 = hi + lo as fp16, channel-major [B, C, Sp] (zero-filled up to Sp)
+    int Sp;
 };
 struct PoolJobs {
     PoolJob job[3];
@@ -43,6 +47,7 @@ struct CoarseParams {
     int B, Sq, Sk, nh, topk;
     int type_a;
     float *tc_ws;               // coarse_tc_workspace_floats() of scratch for the tensor-core kernel, or NULL: fp32 SIMT kernel
+    bool tc_prepped;            // tc_ws already holds Q_lo / K_lo / V^T (written by launch_pool2_tokens, see coarse_tc_operands)
 };
 size_t coarse_smem_bytes(int Sk);
 int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
@@ -50,6 +55,8 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
 bool coarse_tc_applicable(int Sq, int Sk, int topk);
 size_t coarse_tc_workspace_floats(int B, int Sq, int Sk, int C);
 int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream);
+struct CoarseTcOperands { float *q_lo, *k_lo; unsigned short *vt_hi, *vt_lo; int Sp; };
+CoarseTcOperands coarse_tc_operands(float *ws, int B, int Sq, int Sk, int C);      // where those operands live inside tc_ws
 
 // ---- relative position bias of the cascade cross attention, computed where it is consumed
 // (CascadeFeatureTransformer.get_relative_pe, src/model/modules/transformer.py:473-509; casmtr_relpe_desc)

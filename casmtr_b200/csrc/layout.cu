@@ -5,6 +5,8 @@
 // here all (up to 12) maps of one attention call go through ONE batched tile-transpose launch.
 // Token-major makes one (token, head) row exactly one 128-byte line, which is what the gather
 // kernels want.  HBM-bound: 4 B read + 4 B written per element.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -138,49 +140,107 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const __grid_constant_
 }
 
 // Two pyramid levels in one pass (h, w multiples of 4): thread = 4 channels of one level-2 token; its 4x4 block of level-0
-// tokens is read once, the four level-1 averages are written and averaged again (the reference pools the pooled map).
-__global__ void __launch_bounds__(256) pool2_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
+// tokens is read once (all 16 loads in flight), the four level-1 averages are written and averaged again (the reference pools
+// the pooled map).  A warp covers 4 consecutive level-2 tokens x 8 channel quads (every request = four full 128-byte lines), so
+// that the operands the tensor-core coarsest level wants next to the level-2 maps come out of the same pass
+// (qtatt_coarse_tc.cu; coarse_prep_kernel is the stand-alone version): lo2 = x - trunc_tf32(x) of the level-2 map (Q, K), and
+// the level-2 map transposed to channel-major fp16 pairs V * 2^8 = hi + lo (V) -- a 4 x 4 exchange between the four lanes
+// that hold a channel quad of four neighbouring tokens leaves each lane with one channel x 4 tokens = one 8-byte store per half.
+__device__ __forceinline__ float4 avg4(const float4 a, const float4 b, const float4 c, const float4 d) {
+    float4 o;
+    o.x = (((a.x + b.x) + c.x) + d.x) * 0.25f;
+    o.y = (((a.y + b.y) + c.y) + d.y) * 0.25f;
+    o.z = (((a.z + b.z) + c.z) + d.z) * 0.25f;
+    o.w = (((a.w + b.w) + c.w) + d.w) * 0.25f;
+    return o;
+}
+__device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ uint32_t f16_pair(float x) {          // x * 2^8 = hi + lo: hi in bits 0..15, lo in bits 16..31
+    const float xs = fminf(fmaxf(x * 256.f, -65504.f), 65504.f);
+    const __half hi = __float2half_rn(xs);
+    const __half lo = __float2half_rn(xs - __half2float(hi));
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+}
+
+__global__ void __launch_bounds__(256, 2) pool2_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
     __builtin_assume(__isGlobal(jb.src) && __isGlobal(jb.dst) && __isGlobal(jb.dst2));
     const int h1 = jb.h >> 1, w1 = jb.w >> 1, h2 = jb.h >> 2, w2 = jb.w >> 2;
-    const size_t n = (size_t)h2 * w2 * C4;
+    const int n_tok = h2 * w2;
+    const int n_tok_pad = jb.vt_hi ? jb.Sp : n_tok;                // the transposed map is zero-filled up to its padded row length
+    const int per_unit = 4 * C4;                                   // threads per unit of 4 tokens (C4 is a multiple of 8)
+    const size_t n = (size_t)((n_tok_pad + 3) / 4) * per_unit;
     const float4 *src = reinterpret_cast<const float4 *>(jb.src) + (size_t)b * jb.h * jb.w * C4;
     float4 *d1 = reinterpret_cast<float4 *>(jb.dst) + (size_t)b * h1 * w1 * C4;
-    float4 *d2 = reinterpret_cast<float4 *>(jb.dst2) + (size_t)b * n;
+    float4 *d2 = reinterpret_cast<float4 *>(jb.dst2) + (size_t)b * n_tok * C4;
+    float4 *l2 = jb.lo2 ? reinterpret_cast<float4 *>(jb.lo2) + (size_t)b * n_tok * C4 : nullptr;
+    const int lane = threadIdx.x & 31;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        const int t = (int)(i / C4), y = t / w2, x = t - y * w2;
-        float4 m[4];
+        const int u = (int)(i / per_unit), r = (int)(i - (size_t)u * per_unit);
+        const int c = (r >> 5) * 8 + (lane & 7);                   // i - lane is a multiple of 32: r & 31 == lane
+        const int t = 4 * u + (lane >> 3);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < n_tok) {
+            const int y = t / w2, x = t - y * w2;
+            const float4 *p = src + ((size_t)(4 * y) * jb.w + 4 * x) * C4 + c;
+            float4 a[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int y1 = 2 * y + (q >> 1), x1 = 2 * x + (q & 1);
-            const float4 *p = src + ((size_t)(2 * y1) * jb.w + 2 * x1) * C4 + c;
-            const float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)jb.w * C4), d = __ldg(p + (size_t)(jb.w + 1) * C4);
-            m[q].x = (((a.x + bb.x) + cc.x) + d.x) * 0.25f;
-            m[q].y = (((a.y + bb.y) + cc.y) + d.y) * 0.25f;
-            m[q].z = (((a.z + bb.z) + cc.z) + d.z) * 0.25f;
-            m[q].w = (((a.w + bb.w) + cc.w) + d.w) * 0.25f;
-            d1[((size_t)y1 * w1 + x1) * C4 + c] = m[q];
+            for (int q = 0; q < 16; ++q) a[q] = __ldg(p + ((size_t)(q >> 2) * jb.w + (q & 3)) * C4);
+            float4 m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                          // level-1 token (2y + q/2, 2x + q%2): taps in avg_pool2d's window order
+                const int r0 = 2 * (q >> 1), c0 = 2 * (q & 1);
+                m[q] = avg4(a[4 * r0 + c0], a[4 * r0 + c0 + 1], a[4 * (r0 + 1) + c0], a[4 * (r0 + 1) + c0 + 1]);
+                d1[((size_t)(2 * y + (q >> 1)) * w1 + 2 * x + (q & 1)) * C4 + c] = m[q];
+            }
+            o = avg4(m[0], m[1], m[2], m[3]);
+            d2[(size_t)t * C4 + c] = o;
+            if (l2) l2[(size_t)t * C4 + c] = make_float4(tf32_residual(o.x), tf32_residual(o.y), tf32_residual(o.z), tf32_residual(o.w));
         }
-        float4 o;
-        o.x = (((m[0].x + m[1].x) + m[2].x) + m[3].x) * 0.25f;
-        o.y = (((m[0].y + m[1].y) + m[2].y) + m[3].y) * 0.25f;
-        o.z = (((m[0].z + m[1].z) + m[2].z) + m[3].z) * 0.25f;
-        o.w = (((m[0].w + m[1].w) + m[2].w) + m[3].w) * 0.25f;
-        d2[i] = o;
+        if (jb.vt_hi) {                                            // warp-uniform
+            // w[e] = channel 4c + e of token t as an fp16 (hi, lo) pair; 4 x 4 transpose over the lanes {lane & 7} + 8 k:
+            // lane k ends with channel 4c + k of tokens 4u .. 4u + 3
+            uint32_t w[4] = {f16_pair(o.x), f16_pair(o.y), f16_pair(o.z), f16_pair(o.w)};
+            const int k = lane >> 3;
+            {
+                const bool up = k & 2;                             // exchange 2 x 2 blocks with lane ^ 16
+                const uint32_t s0 = up ? w[0] : w[2], s1 = up ? w[1] : w[3];
+                const uint32_t r0 = __shfl_xor_sync(FULL_MASK, s0, 16), r1 = __shfl_xor_sync(FULL_MASK, s1, 16);
+                if (up) { w[0] = r0; w[1] = r1; } else { w[2] = r0; w[3] = r1; }
+            }
+            {
+                const bool up = k & 1;                             // exchange single elements with lane ^ 8
+                const uint32_t s0 = up ? w[0] : w[1], s1 = up ? w[2] : w[3];
+                const uint32_t r0 = __shfl_xor_sync(FULL_MASK, s0, 8), r1 = __shfl_xor_sync(FULL_MASK, s1, 8);
+                if (up) { w[0] = r0; w[2] = r1; } else { w[1] = r0; w[3] = r1; }
+            }
+            // after the two steps w[m] of lane k = (token 4u + m', channel ...): see the index algebra in tests (bit-exact vs coarse_prep_kernel)
+            const size_t row = ((size_t)b * 4 * C4 + 4 * c + k) * jb.Sp + 4 * u;
+            const uint2 hi = make_uint2((w[0] & 0xffffu) | (w[1] << 16), (w[2] & 0xffffu) | (w[3] << 16));
+            const uint2 lo = make_uint2((w[0] >> 16) | (w[1] & 0xffff0000u), (w[2] >> 16) | (w[3] & 0xffff0000u));
+            if (4 * u < jb.Sp) {
+                *reinterpret_cast<uint2 *>(jb.vt_hi + row) = hi;
+                *reinterpret_cast<uint2 *>(jb.vt_lo + row) = lo;
+            }
+        }
     }
 }
 
 int launch_pool2_tokens(const PoolJobs &jobs, int B, int C, cudaStream_t stream) {
     if (jobs.n == 0 || B == 0) return CASMTR_OK;
-    CASMTR_REQUIRE(C % 4 == 0, CASMTR_E_UNSUPPORTED, "pool_tokens: C=%d must be a multiple of 4", C);
+    CASMTR_REQUIRE(C % 32 == 0, CASMTR_E_UNSUPPORTED, "pool2_tokens: C=%d must be a multiple of 32", C);
     size_t nmax = 0;
     for (int i = 0; i < jobs.n; ++i) {
-        CASMTR_REQUIRE((((uintptr_t)jobs.job[i].src | (uintptr_t)jobs.job[i].dst | (uintptr_t)jobs.job[i].dst2) & 15) == 0, CASMTR_E_INVALID, "pool_tokens: unaligned map");
-        CASMTR_REQUIRE(jobs.job[i].h % 4 == 0 && jobs.job[i].w % 4 == 0, CASMTR_E_INVALID, "pool2_tokens: grid not a multiple of 4");
-        nmax = std::max(nmax, (size_t)(jobs.job[i].h / 4) * (jobs.job[i].w / 4) * (C / 4));
+        const PoolJob &jb = jobs.job[i];
+        CASMTR_REQUIRE((((uintptr_t)jb.src | (uintptr_t)jb.dst | (uintptr_t)jb.dst2 | (uintptr_t)jb.lo2 | (uintptr_t)jb.vt_hi | (uintptr_t)jb.vt_lo) & 15) == 0,
+                       CASMTR_E_INVALID, "pool_tokens: unaligned map");
+        CASMTR_REQUIRE(jb.h % 4 == 0 && jb.w % 4 == 0, CASMTR_E_INVALID, "pool2_tokens: grid not a multiple of 4");
+        CASMTR_REQUIRE((jb.vt_hi == nullptr) == (jb.vt_lo == nullptr), CASMTR_E_INVALID, "pool2_tokens: both halves of the transposed map or none");
+        const int n_tok = (jb.h / 4) * (jb.w / 4);
+        CASMTR_REQUIRE(jb.vt_hi == nullptr || (jb.Sp % 4 == 0 && jb.Sp >= n_tok), CASMTR_E_INVALID, "pool2_tokens: padded row length %d", jb.Sp);
+        nmax = std::max(nmax, (size_t)(((jb.vt_hi ? jb.Sp : n_tok) + 3) / 4) * C);
     }
     if (nmax == 0) return CASMTR_OK;
     LaunchScope ls(CASMTR_K_LAYOUT, stream);

@@ -30,6 +30,7 @@
 // coarse_match.cu; the top-k sets are those of the fp32 reference except at fp32 near-ties (tests/: sets + the tie rule).
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -696,6 +697,17 @@ size_t coarse_tc_workspace_floats(int B, int Sq, int Sk, int C) {
     return align_up((size_t)B * Sq * C, 64) + align_up((size_t)B * Sk * C, 64) + 2 * align_up((size_t)B * C * Sp / 2, 64);
 }
 
+CoarseTcOperands coarse_tc_operands(float *ws, int B, int Sq, int Sk, int C) {
+    CoarseTcOperands o;
+    o.Sp = (Sk + 7) / 8 * 8;
+    o.q_lo = ws;
+    o.k_lo = o.q_lo + align_up((size_t)B * Sq * C, 64);
+    float *vh = o.k_lo + align_up((size_t)B * Sk * C, 64);
+    o.vt_hi = reinterpret_cast<unsigned short *>(vh);
+    o.vt_lo = reinterpret_cast<unsigned short *>(vh + align_up((size_t)B * C * o.Sp / 2, 64));
+    return o;
+}
+
 int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream) {
     int nv, n_kb;
     tc_variant(p.Sk, nv, n_kb);
@@ -703,15 +715,15 @@ int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream
     CASMTR_REQUIRE(nv != 0, CASMTR_E_UNSUPPORTED, "coarse level with %d keys is outside the tensor-core kernel", p.Sk);
     CASMTR_REQUIRE((((uintptr_t)p.q | (uintptr_t)p.k | (uintptr_t)p.v | (uintptr_t)ws) & 15) == 0, CASMTR_E_INVALID, "coarse level operands must be 16-byte aligned");
     const int C = p.nh * D;
-    const int Sp = (p.Sk + 7) / 8 * 8;
-    float *q_lo = ws;
-    float *k_lo = q_lo + align_up((size_t)p.B * p.Sq * C, 64);
-    __half *vt_hi = reinterpret_cast<__half *>(k_lo + align_up((size_t)p.B * p.Sk * C, 64));
-    __half *vt_lo = reinterpret_cast<__half *>(reinterpret_cast<float *>(vt_hi) + align_up((size_t)p.B * C * Sp / 2, 64));
-    {
+    const CoarseTcOperands op = coarse_tc_operands(ws, p.B, p.Sq, p.Sk, C);
+    const int Sp = op.Sp;
+    float *q_lo = op.q_lo, *k_lo = op.k_lo;
+    __half *vt_hi = reinterpret_cast<__half *>(op.vt_hi), *vt_lo = reinterpret_cast<__half *>(op.vt_lo);
+    if (!p.tc_prepped) {                                         // callers that pooled the pyramid here already wrote them (pool2_tokens_kernel)
         LaunchScope ls(CASMTR_K_LAYOUT, stream);
         const int nq4 = p.Sq * C / 4, nk4 = p.Sk * C / 4;
-        launch_k(coarse_prep_kernel, dim3(48, 2, p.B), 256, 0, stream, p.q, p.k, p.v, q_lo, k_lo, vt_hi, vt_lo, p.Sq, p.Sk, Sp, C, nq4, nk4);
+        const int tiles = (C / 32) * ((Sp + 31) / 32);           // one transposed tile per CTA, the residuals in at most two sweeps
+        launch_k(coarse_prep_kernel, dim3((unsigned)std::max(tiles, 48), 2, p.B), 256, 0, stream, p.q, p.k, p.v, q_lo, k_lo, vt_hi, vt_lo, p.Sq, p.Sk, Sp, C, nq4, nk4);
         CASMTR_CHECK_LAUNCH("coarse_prep_kernel");
     }
     CoarseTcMaps maps;
