@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const __grid_constant_
 }
 
 // Two pyramid levels in one pass (h, w multiples of 4): thread = 4 channels of one level-2 token; its 4x4 block of level-0
-// tokens is read once (all 16 loads in flight), the four level-1 averages are written and averaged again (the reference pools
+// tokens is read once (two rows = 8 loads in flight at a time), the four level-1 averages are written and averaged again (the reference pools
 // the pooled map).  A warp covers 4 consecutive level-2 tokens x 8 channel quads (every request = four full 128-byte lines), so
 // that the operands the tensor-core coarsest level wants next to the level-2 maps come out of the same pass
 // (qtatt_coarse_tc.cu; coarse_prep_kernel is the stand-alone version): lo2 = x - trunc_tf32(x) of the level-2 map (Q, K), and
@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t f16_pair(float x) {          // x * 2^8 = hi
     return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
 }
 
-__global__ void __launch_bounds__(256, 2) pool2_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
+__global__ void __launch_bounds__(256, 4) pool2_tokens_kernel(const __grid_constant__ PoolJobs jobs, int C4) {
     pdl_sync();
     const int j = blockIdx.z, b = blockIdx.y;
     const PoolJob jb = jobs.job[j];
@@ -185,15 +185,17 @@ __global__ void __launch_bounds__(256, 2) pool2_tokens_kernel(const __grid_const
         if (t < n_tok) {
             const int y = t / w2, x = t - y * w2;
             const float4 *p = src + ((size_t)(4 * y) * jb.w + 4 * x) * C4 + c;
-            float4 a[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) a[q] = __ldg(p + ((size_t)(q >> 2) * jb.w + (q & 3)) * C4);
             float4 m[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                          // level-1 token (2y + q/2, 2x + q%2): taps in avg_pool2d's window order
-                const int r0 = 2 * (q >> 1), c0 = 2 * (q & 1);
-                m[q] = avg4(a[4 * r0 + c0], a[4 * r0 + c0 + 1], a[4 * (r0 + 1) + c0], a[4 * (r0 + 1) + c0 + 1]);
-                d1[((size_t)(2 * y + (q >> 1)) * w1 + 2 * x + (q & 1)) * C4 + c] = m[q];
+            for (int half = 0; half < 2; ++half) {                 // two level-0 rows at a time: 8 loads in flight, 64 registers, 4 CTAs per SM
+                float4 a[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[q] = __ldg(p + ((size_t)(2 * half + (q >> 2)) * jb.w + (q & 3)) * C4);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {                      // level-1 token (2y + half, 2x + e): taps in avg_pool2d's window order
+                    m[2 * half + e] = avg4(a[2 * e], a[2 * e + 1], a[4 + 2 * e], a[4 + 2 * e + 1]);
+                    d1[((size_t)(2 * y + half) * w1 + 2 * x + e) * C4 + c] = m[2 * half + e];
+                }
             }
             o = avg4(m[0], m[1], m[2], m[3]);
             d2[(size_t)t * C4 + c] = o;

@@ -177,14 +177,19 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     __syncwarp();                                   // K slab and Q are dead from here on (A2 / staging alias them)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int c = 32 * r + lane;
-        const bool valid = c < KC;
+        const bool valid = 32 * r + lane < KC;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            float s = sc[r][f] * scale;
-            if (CASCADE && p.rel_pos != nullptr && valid)
-                s += __ldg(p.rel_pos + (((size_t)b * p.nh + h) * L0 + QTOK(f)) * KC + c);
-            sc[r][f] = valid ? s : -INFINITY;
+        for (int f = 0; f < 4; ++f) sc[r][f] = valid ? sc[r][f] * scale : -INFINITY;
+    }
+    if (CASCADE && p.rel_pos != nullptr) {          // relative position bias read as a tensor (one test per item, not per score)
+        const float *rp = p.rel_pos + ((size_t)b * p.nh + h) * L0 * KC;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int c = 32 * r + lane;
+            if (c < KC) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) sc[r][f] += __ldg(rp + (size_t)QTOK(f) * KC + c);
+            }
         }
     }
     if (CASCADE && PE) {                            // the same bias from its embedding tables (get_relative_pe, transformer.py:473-509)
