@@ -331,7 +331,9 @@ struct TcParams {
     int levels, n_weights;
     int B, Sq, Sk, nh, topk;
     int n_kb;                   // k-blocks of 32 keys in the slab (even)
-    long long *dbg;             // CASMTR_TC_DEBUG=1: phase timestamps of CTA (0,0) (development aid, NULL otherwise)
+    int n_big, rows_small;      // row tiles of a (batch, head): blockIdx.y < n_big covers 64 rows, the tiles after them rows_small (even) each
+    long long *dbg;             // CASMTR_TC_DEBUG=1: phase timestamps of tile dbg_tile of (batch 0, head 0) (development aid, NULL otherwise)
+    int dbg_tile;
 };
 
 constexpr int ROWS = 64;
@@ -357,8 +359,14 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
     uint32_t *tmem_slot = (uint32_t *)(pvdone + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y / p.nh, h = blockIdx.y % p.nh;
-    const int row0 = blockIdx.x * ROWS;
+    // Row tiles: grid.x = (batch, head), grid.y = tile.  CTAs are dispatched x-fastest, so every 64-row tile is handed out before the
+    // first short one: the launcher sizes the 64-row tiles to whole waves of SMs and splits the remaining rows of every (batch, head)
+    // evenly over one more wave of short tiles (tc_row_tiles) instead of leaving a second wave that is mostly idle SMs.
+    const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
+    const int tile = blockIdx.y;
+    const int row0 = tile < p.n_big ? tile * ROWS : p.n_big * ROWS + (tile - p.n_big) * p.rows_small;
+    const int n_rows = min(tile < p.n_big ? ROWS : p.rows_small, p.Sq - row0);     // rows of the 64-row MMA tile this CTA owns
+    if (n_rows <= 0) return;
     const int C = p.nh * D;
     const int n_chunks = (p.n_kb + 3) / 4;
 
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
     const uint32_t tmem_o = tmem_base + 2 * SCH;
 
     uint8_t *q_hi = stage, *q_lo = stage + 8192;
-#define TC_STAMP(i) do { if (p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[i] = clock64(); } while (0)
+#define TC_STAMP(i) do { if (p.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) p.dbg[i] = clock64(); } while (0)
     TC_STAMP(0);
     // V^T block j (64 keys: hi 4 KB + lo 4 KB, fp16) travels through slot (j + V_LEAD) % N_VSLOT.  A slot's u-th use waits for parity
     // u & 1 (full) / (u & 1) ^ 1 (empty); slots 0 and 1 (the selection lists' bytes during phase T) are first used by blocks 4, 5.
@@ -483,11 +491,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
 
     // ================================================================ phase T: soft-max + top-k, one warp per row
     {
-        constexpr int RPW = ROWS / NWARP;                        // 4 rows per warp
         constexpr int RP = 2;
         float *lval = (float *)stage + warp * 2 * LIST_CAP;      // two survivor lists per warp (16 KB in all = V slots 0, 1)
         int *lpos = (int *)(stage + NWARP * 2 * LIST_CAP * 4) + warp * 2 * LIST_CAP;
-        for (int j0 = 0; j0 < RPW; j0 += RP) {
+        // pass j: warp w takes rows 32 j + 2 w, + 1 -- a short tile keeps as many warps busy as it has row pairs
+        for (int j0 = RP * warp; j0 < n_rows; j0 += RP * NWARP) {
             int row[RP];
             bool live[RP];
             float *lvp[RP];
@@ -497,8 +505,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
             bool keep_a[RP], keep_b[RP];
 #pragma unroll
             for (int rr = 0; rr < RP; ++rr) {
-                row[rr] = warp * RPW + j0 + rr;
-                live[rr] = row0 + row[rr] < p.Sq;
+                row[rr] = j0 + rr;
+                live[rr] = row[rr] < n_rows;
                 lvp[rr] = lval + rr * LIST_CAP;
                 lpp[rr] = lpos + rr * LIST_CAP;
             }
@@ -567,15 +575,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
             for (int l = 0; l < p.n_weights; ++l) mx = fmaxf(mx, __ldg(p.level_weight + l));
             for (int l = 0; l < p.n_weights; ++l) den += expf(__ldg(p.level_weight + l) - mx);
             w0 = expf(__ldg(p.level_weight) - mx) / den;
-            if (p.wsm && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane < p.levels)      // the finer levels read their weight from here
+            if (p.wsm && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane < p.levels)      // the finer levels read their weight from here (tile 0 always exists)
                 p.wsm[lane] = expf(__ldg(p.level_weight + lane) - mx) / den;
         }
         mbar_wait(pvdone, 0);
         tc_fence_after();
-        if (warp == 4 && lane == 0 && p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[3] = clock64();
+        if (warp == 4 && lane == 0 && p.dbg && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) p.dbg[3] = clock64();
         float v[32];
         tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16), v);
-        if (lane < 16 && row0 + r < p.Sq) {
+        if (lane < 16 && r < n_rows) {
             const float f = w0 / (rsum[r] * (P_SCALE * V_SCALE));
             float *dst = p.acc + ((size_t)b * p.Sq + row0 + r) * C + h * D;
 #pragma unroll
@@ -664,6 +672,27 @@ void tc_variant(int Sk, int &nv, int &n_kb) {
     nv = n_kb <= 8 ? 8 : (n_kb <= 16 ? 16 : (n_kb <= 22 ? 22 : 0));
 }
 
+// Row tiles of one (batch, head) for a grid of `bh` of them on n_sm SMs (one CTA per SM).  Plain tiling = floor(Sq / 64) tiles of 64
+// rows + the remainder.  When that makes 1 - 3 full waves plus a mostly idle one (one or two image pairs per launch), the 64-row
+// tiles are cut back to whole waves and the rows left over in every (batch, head) are split evenly over one more wave of short tiles:
+// 832^2, one pair: 9 x 64 + 9 x 12 rows per head (a wave of long CTAs, then a wave of CTAs whose row phase is a fifth as long) instead
+// of 10 x 64 + 36 = 176 CTAs on 148 SMs.
+void tc_row_tiles(int Sq, int bh, int n_sm, int &n_big, int &n_small, int &rows_small) {
+    const int n_full = Sq / ROWS, plain = (Sq + ROWS - 1) / ROWS;
+    n_big = n_full; n_small = plain - n_full; rows_small = ((Sq - n_full * ROWS) + 1) & ~1;
+    static const bool balance = [] { const char *e = getenv("CASMTR_TC_BALANCE"); return !(e && e[0] == '0'); }();
+    const long long waves = (long long)bh * plain / n_sm;
+    if (!balance || waves < 1 || waves > 3 || (long long)bh * plain % n_sm == 0) return;
+    const int nb = (int)std::min<long long>(n_full, waves * n_sm / bh);
+    if (nb < 1) return;
+    const int left = Sq - nb * ROWS;
+    if (left <= 0) { n_big = nb; n_small = 0; rows_small = 0; return; }
+    int ns = std::max(1, n_sm / bh);
+    int rs = ((left + ns - 1) / ns + 1) & ~1;
+    if (rs > ROWS) { ns = (left + ROWS - 1) / ROWS; rs = ((left + ns - 1) / ns + 1) & ~1; }
+    n_big = nb; n_small = ns; rows_small = rs;
+}
+
 template <int NV>
 int launch_variant(const CoarseTcMaps &maps, const TcParams &tp, bool type_a, int grid_x, int grid_y, size_t smem, cudaStream_t stream) {
     static PerDeviceOnce once;
@@ -743,8 +772,11 @@ int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream
     tp.dbg = dbg_on ? dbg_buf : nullptr;
     const size_t smem = tc_smem_bytes(n_kb);
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED, "coarse tensor-core kernel: %zu bytes of shared memory", smem);
-    CASMTR_REQUIRE((long long)p.B * p.nh <= 65535, CASMTR_E_UNSUPPORTED, "coarse level: batch x heads too large");
-    const int gx = (p.Sq + rows - 1) / rows, gy = p.B * p.nh;
+    int n_big, n_small, rows_small;
+    tc_row_tiles(p.Sq, p.B * p.nh, casmtr_sm_count(), n_big, n_small, rows_small);
+    tp.n_big = n_big; tp.rows_small = rows_small;
+    if (tp.dbg) { static const int t = [] { const char *e = getenv("CASMTR_TC_DEBUG_TILE"); return e ? atoi(e) : 0; }(); tp.dbg_tile = t; }
+    const int gx = p.B * p.nh, gy = n_big + n_small;
     const bool a = p.type_a != 0;
     if (nv == 8) rc = launch_variant<8>(maps, tp, a, gx, gy, smem, stream);
     else if (nv == 16) rc = launch_variant<16>(maps, tp, a, gx, gy, smem, stream);
