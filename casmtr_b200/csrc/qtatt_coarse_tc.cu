@@ -43,6 +43,7 @@ using namespace tma;
 constexpr int D = 32;
 constexpr int NWARP = 16;
 constexpr int LIST_CAP = 64;
+constexpr int LIST_KEY_OFF = NWARP * 2 * LIST_CAP * 4;      // bytes from a warp's survivor VALUE list to its KEY list (phase T: values of all warps, then keys)
 constexpr int STAGE_AREA = 48 * 1024;           // Q_hi, Q_lo (8 KB each) in phase S, the selection lists (16 KB) in phase T, the V^T ring throughout T / PV
 
 struct CoarseTcMaps { CUtensorMap q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo; };
@@ -179,8 +180,11 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
 template <int NV, int RP>
 __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row)[RP], const bool (&live)[RP], int Sk, int n_blk, int k, int lane,
                                                    float *const (&lv)[RP], int *const (&lp)[RP], float (&sum)[RP],
-                                                   float (&va)[RP], float (&vb)[RP], int (&pa)[RP], int (&pb)[RP], bool (&keep_a)[RP], bool (&keep_b)[RP]) {
+                                                   float (&va)[RP], float (&vb)[RP], int (&pa)[RP], int (&pb)[RP], bool (&keep_a)[RP], bool (&keep_b)[RP],
+                                                   long long *dbg = nullptr) {
     constexpr int NB = NV / 2;
+#define T_STAMP(i) do { if (dbg && lane == 0) dbg[i] = clock64(); } while (0)
+    T_STAMP(8);
     float e[RP][NV];
     float m[RP];
     uint8_t *pbase[RP];
@@ -202,6 +206,7 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) m[rr] = warp_max(m[rr]);
     __syncwarp();                                                 // every lane holds its part of the rows: the bytes may be overwritten
+    T_STAMP(9);
     float m1[RP], m2[RP];
     const int full_blk = Sk >> 6;                                 // 64-key blocks without a padding column
 #pragma unroll
@@ -231,6 +236,7 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
     }
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) sum[rr] = warp_sum(sum[rr]);
+    T_STAMP(10);
     // T = k-th largest of the 64 lane-top-2 values: max(sorted-descending m1, sorted-ascending m2) is the upper half of their union
     float T[RP];
     {
@@ -257,7 +263,10 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
             else T[rr] = __shfl_sync(FULL_MASK, warp_merge_desc(tt, lane), k - 1);
         }
     }
+    T_STAMP(11);
     // survivors {P >= T}: per-lane count, warp prefix sum, compaction into the warp's list
+    // (straight-line predicated code: the branchy version of this loop -- if (e >= T) { if (pos < cap) store; ++pos; } -- cost 4.5 K of the
+    // 13 K cycles a row pair takes, CASMTR_TC_DEBUG=1)
     int n[RP];
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) {
@@ -271,16 +280,28 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
             if (lane >= o) inc += u;
         }
         n[rr] = __shfl_sync(FULL_MASK, inc, 31);
-        int pos = inc - cnt;
+        if (n[rr] <= LIST_CAP) {                                  // warp-uniform; longer lists take the exact slow path below and are never read
+            // lane's survivors go to list entries [inc - cnt, inc): one running shared-memory address, the key list LIST_KEY_OFF bytes after the value list
+            uint32_t addr = smem_u32(lv[rr]) + 4u * (uint32_t)(inc - cnt);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            if (e[rr][i] >= T[rr]) {
-                if (pos < LIST_CAP) { lv[rr][pos] = e[rr][i]; lp[rr][pos] = 64 * (i >> 1) + t + (i & 1); }
-                ++pos;
+            for (int i = 0; i < NV; ++i) {
+                const int key = 64 * (i >> 1) + t + (i & 1);
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred q;\n\t"
+                    "setp.ge.f32 q, %1, %2;\n\t"
+                    "@q st.shared.f32 [%0], %1;\n\t"
+                    "@q st.shared.s32 [%0 + %4], %3;\n\t"
+                    "@q add.u32 %0, %0, 4;\n\t"
+                    "}\n"
+                    : "+r"(addr)
+                    : "f"(e[rr][i]), "f"(T[rr]), "r"(key), "n"(LIST_KEY_OFF)
+                    : "memory");
             }
         }
     }
     __syncwarp();
+    T_STAMP(12);
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) {
         keep_a[rr] = keep_b[rr] = false;
@@ -320,6 +341,9 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
         }
     }
     __syncwarp();
+    T_STAMP(13);
+    if (dbg && lane == 0) { dbg[14] = n[0]; dbg[15] = n[RP - 1]; }
+#undef T_STAMP
 }
 
 struct TcParams {
@@ -493,7 +517,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
     {
         constexpr int RP = 2;
         float *lval = (float *)stage + warp * 2 * LIST_CAP;      // two survivor lists per warp (16 KB in all = V slots 0, 1)
-        int *lpos = (int *)(stage + NWARP * 2 * LIST_CAP * 4) + warp * 2 * LIST_CAP;
+        int *lpos = (int *)(stage + LIST_KEY_OFF) + warp * 2 * LIST_CAP;
         // pass j: warp w takes rows 32 j + 2 w, + 1 -- a short tile keeps as many warps busy as it has row pairs
         for (int j0 = RP * warp; j0 < n_rows; j0 += RP * NWARP) {
             int row[RP];
@@ -510,7 +534,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
                 lvp[rr] = lval + rr * LIST_CAP;
                 lpp[rr] = lpos + rr * LIST_CAP;
             }
-            rows_softmax_topk<NV, RP>(sm, row, live, p.Sk, p.n_kb / 2, p.topk, lane, lvp, lpp, sum, va, vb, pa, pb, keep_a, keep_b);
+            long long *tdbg = (p.dbg && warp == 0 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) ? p.dbg : nullptr;
+            rows_softmax_topk<NV, RP>(sm, row, live, p.Sk, p.n_kb / 2, p.topk, lane, lvp, lpp, sum, va, vb, pa, pb, keep_a, keep_b, tdbg);
 #pragma unroll
             for (int rr = 0; rr < RP; ++rr) {
                 if (!live[rr]) continue;                     // warp-uniform
@@ -532,6 +557,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
                     if (TYPE_A) p16_zero(sm, row[rr], pb[rr]);
                 }
             }
+            if (tdbg && lane == 0) tdbg[16] = clock64();
         }
     }
     fence_async_smem();                                          // P in the slab -> visible to the tensor core's operand reads
@@ -768,7 +794,7 @@ int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream
     tp.levels = p.levels; tp.n_weights = p.n_weights; tp.B = p.B; tp.Sq = p.Sq; tp.Sk = p.Sk; tp.nh = p.nh; tp.topk = p.topk; tp.n_kb = n_kb;
     static const bool dbg_on = [] { const char *e = getenv("CASMTR_TC_DEBUG"); return e && e[0] == '1'; }();
     static long long *dbg_buf = nullptr;
-    if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 24 * sizeof(long long));
     tp.dbg = dbg_on ? dbg_buf : nullptr;
     const size_t smem = tc_smem_bytes(n_kb);
     CASMTR_REQUIRE(smem <= 227 * 1024, CASMTR_E_UNSUPPORTED, "coarse tensor-core kernel: %zu bytes of shared memory", smem);
@@ -782,11 +808,13 @@ int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream
     else if (nv == 16) rc = launch_variant<16>(maps, tp, a, gx, gy, smem, stream);
     else rc = launch_variant<22>(maps, tp, a, gx, gy, smem, stream);
     if (tp.dbg && rc == CASMTR_OK) {                 // development aid: synchronises, never on in the product path
-        long long t[8];
+        long long t[24];
         cudaStreamSynchronize(stream);
         cudaMemcpy(t, tp.dbg, sizeof(t), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[tc coarse %dx%d rows=%d] cycles: S %lld  T %lld  PV %lld  epilogue %lld  total %lld\n", p.Sq, p.Sk, rows,
                 t[1] - t[0], t[2] - t[1], t[3] - t[2], t[5] - t[3], t[5] - t[0]);
+        fprintf(stderr, "[tc coarse phase T, warp 0, first row pair] load+max %lld  exp+pack %lld  threshold %lld  compaction %lld  trim %lld  (survivors %lld, %lld)  [start +%lld after phase S, outputs until +%lld]\n",
+                t[9] - t[8], t[10] - t[9], t[11] - t[10], t[12] - t[11], t[13] - t[12], t[14], t[15], t[8] - t[1], t[16] - t[13]);
     }
     return rc;
 }
