@@ -267,25 +267,40 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
     // survivors {P >= T}: per-lane count, warp prefix sum, compaction into the warp's list
     // (straight-line predicated code: the branchy version of this loop -- if (e >= T) { if (pos < cap) store; ++pos; } -- cost 4.5 K of the
     // 13 K cycles a row pair takes, CASMTR_TC_DEBUG=1)
-    int n[RP];
+    // The rows of the pair are interleaved by hand below (counts, scans, stores, trim rounds): each is a dependent chain, and the
+    // shuffles / volatile stores pin the order the compiler may issue them in.
+    int n[RP], cnt[RP], inc[RP];
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) {
-        int cnt = 0;
+        cnt[rr] = 0;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) cnt += e[rr][i] >= T[rr];
-        int inc = cnt;
+        for (int i = 0; i < NV; ++i) cnt[rr] += e[rr][i] >= T[rr];
+        inc[rr] = cnt[rr];
+    }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(FULL_MASK, inc, o);
-            if (lane >= o) inc += u;
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr) {
+            const int u = __shfl_up_sync(FULL_MASK, inc[rr], o);
+            if (lane >= o) inc[rr] += u;
         }
-        n[rr] = __shfl_sync(FULL_MASK, inc, 31);
-        if (n[rr] <= LIST_CAP) {                                  // warp-uniform; longer lists take the exact slow path below and are never read
-            // lane's survivors go to list entries [inc - cnt, inc): one running shared-memory address, the key list LIST_KEY_OFF bytes after the value list
-            uint32_t addr = smem_u32(lv[rr]) + 4u * (uint32_t)(inc - cnt);
+    }
+    {
+        // lane's survivors go to list entries [inc - cnt, inc): one running shared-memory address per row, the key list LIST_KEY_OFF
+        // bytes after the value list.  Lists longer than LIST_CAP are never read (exact slow path below): their threshold becomes +inf.
+        uint32_t addr[RP];
+        float Ts[RP];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int key = 64 * (i >> 1) + t + (i & 1);
+        for (int rr = 0; rr < RP; ++rr) {
+            n[rr] = __shfl_sync(FULL_MASK, inc[rr], 31);
+            addr[rr] = smem_u32(lv[rr]) + 4u * (uint32_t)(inc[rr] - cnt[rr]);
+            Ts[rr] = n[rr] <= LIST_CAP ? T[rr] : INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int key = 64 * (i >> 1) + t + (i & 1);
+#pragma unroll
+            for (int rr = 0; rr < RP; ++rr)
                 asm volatile(
                     "{\n\t"
                     ".reg .pred q;\n\t"
@@ -294,31 +309,40 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
                     "@q st.shared.s32 [%0 + %4], %3;\n\t"
                     "@q add.u32 %0, %0, 4;\n\t"
                     "}\n"
-                    : "+r"(addr)
-                    : "f"(e[rr][i]), "f"(T[rr]), "r"(key), "n"(LIST_KEY_OFF)
+                    : "+r"(addr[rr])
+                    : "f"(e[rr][i]), "f"(Ts[rr]), "r"(key), "n"(LIST_KEY_OFF)
                     : "memory");
-            }
         }
     }
     __syncwarp();
     T_STAMP(12);
+    int rem[RP], rounds = 0;                                      // survivors to drop per row (fast path), and the longest of them
 #pragma unroll
     for (int rr = 0; rr < RP; ++rr) {
-        keep_a[rr] = keep_b[rr] = false;
-        va[rr] = vb[rr] = 0.f; pa[rr] = pb[rr] = 0;
-        if (n[rr] <= LIST_CAP && n[rr] >= k) {
-            keep_a[rr] = lane < n[rr]; keep_b[rr] = lane + 32 < n[rr];
-            va[rr] = keep_a[rr] ? lv[rr][lane] : 0.f; pa[rr] = keep_a[rr] ? lp[rr][lane] : 0;
-            vb[rr] = keep_b[rr] ? lv[rr][lane + 32] : 0.f; pb[rr] = keep_b[rr] ? lp[rr][lane + 32] : 0;
-            for (int r = n[rr]; r > k; --r) {               // drop the smallest survivor (ties: lowest lane, first list half)
-                const float lm = fminf(keep_a[rr] ? va[rr] : INFINITY, keep_b[rr] ? vb[rr] : INFINITY);
-                const float gm = warp_min(lm);
-                const int owner = __ffs(__ballot_sync(FULL_MASK, lm == gm)) - 1;
-                if (lane == owner) {
-                    if (keep_a[rr] && va[rr] == gm) keep_a[rr] = false; else keep_b[rr] = false;
-                }
-            }
-        } else if (live[rr]) {
+        const bool fast = n[rr] <= LIST_CAP && n[rr] >= k;
+        keep_a[rr] = fast && lane < n[rr]; keep_b[rr] = fast && lane + 32 < n[rr];
+        va[rr] = keep_a[rr] ? lv[rr][lane] : 0.f; pa[rr] = keep_a[rr] ? lp[rr][lane] : 0;
+        vb[rr] = keep_b[rr] ? lv[rr][lane + 32] : 0.f; pb[rr] = keep_b[rr] ? lp[rr][lane + 32] : 0;
+        rem[rr] = fast ? n[rr] - k : 0;
+        rounds = max(rounds, rem[rr]);
+    }
+    for (int it = 0; it < rounds; ++it) {                         // drop the smallest survivor (ties: lowest lane, first list half)
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr) {
+            // P >= 0: the bit patterns order like the values, so the warp minimum is an integer REDUX (and +inf = 0x7f800000 stays on top)
+            const unsigned ua = keep_a[rr] ? __float_as_uint(va[rr]) : 0x7f800000u, ub = keep_b[rr] ? __float_as_uint(vb[rr]) : 0x7f800000u;
+            const unsigned lm = min(ua, ub);
+            const unsigned gm = __reduce_min_sync(FULL_MASK, lm);
+            const unsigned first = __ballot_sync(FULL_MASK, lm == gm);
+            const bool mine = it < rem[rr] && (first & ((1u << lane) - 1u)) == 0 && lm == gm;      // lowest lane holding the minimum
+            const bool drop_a = mine && ua == gm;
+            keep_b[rr] = keep_b[rr] && !(mine && !drop_a);
+            keep_a[rr] = keep_a[rr] && !drop_a;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RP; ++rr) {
+        if (!(n[rr] <= LIST_CAP && n[rr] >= k) && live[rr]) {
             // massive ties (more than LIST_CAP entries share the k-th value): k rounds of warp arg-max over the registers, exact but
             // slow; ties go to the lowest lane, then the lowest element
             for (int it = 0; it < k; ++it) {
