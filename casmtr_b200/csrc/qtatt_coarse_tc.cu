@@ -390,6 +390,7 @@ constexpr int SCH = 128;                        // keys per S chunk (UMMA N); th
 constexpr int MAX_SCHUNK = 6;                   // n_kb <= 22 -> at most 5 chunks of 4 k-blocks + 1 of 2
 constexpr int V_SLOT = 8192;                    // one 64-key block of V^T in fp16: hi 4 KB + lo 4 KB
 constexpr int N_VSLOT = STAGE_AREA / V_SLOT;    // 6
+constexpr int N_DRAIN = 8;                      // warps 4 .. 11 drain the S accumulators (phase S)
 constexpr int V_LEAD = 2;                       // block j lives in slot (j + V_LEAD) % N_VSLOT: slots 0, 1 hold the selection lists during phase T
 
 template <int NV, bool TYPE_A>
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
     if (tid == 0) {
         mbar_init(qfull, 1);
         for (int s = 0; s < MAX_SCHUNK; ++s) mbar_init(kfull + s, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, N_DRAIN); }
         for (int s = 0; s < N_VSLOT; ++s) { mbar_init(vfull + s, 1); mbar_init(vempty + s, 1); }
         mbar_init(pvdone, 1);
     }
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
         const CUtensorMap *tm = lane == 0 ? &maps.q_hi : lane == 1 ? &maps.q_lo : lane == 2 ? &maps.k_hi : lane == 3 ? &maps.k_lo : lane == 4 ? &maps.vt_hi : &maps.vt_lo;
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
     }
-    if (warp == 1) {                                            // TMEM: 2 S accumulators of 128 columns, O in the 32 columns after them
+    if (warp == 1) {                                            // TMEM: 2 S accumulators of 128 columns, O in the 64 columns after them
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -500,9 +501,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
                 umma_commit(tfull + a);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // drain: TMEM lane quarter q holds rows 16 q .. 16 q + 15 of the 64-row accumulator in its first 16 lanes (M = 64 layout)
-        const int q = warp & 3;
+    } else if (warp >= 4 && warp < 4 + N_DRAIN) {
+        // drain: TMEM lane quarter q holds rows 16 q .. 16 q + 15 of the 64-row accumulator in its first 16 lanes (M = 64 layout).
+        // A warp reaches the quarter warp % 4 only, so two warps share each quarter and take alternate k-blocks of a chunk: with
+        // one warp per quarter the drain (7 K cycles per tile) was longer than the MMAs it follows (4.6 K).
+        const int q = warp & 3, part = (warp - 4) >> 2;
         const int r = 16 * q + lane;                             // accumulator row of this thread (lanes >= 16: none)
         const bool mine = lane < 16;
         const float scale = rsqrtf((float)D) * LOG2E_F;          // logits in base 2: P = 2^(s - max) needs no multiply per element
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
             const int nk = min(4, p.n_kb - 4 * c);
             mbar_wait(tfull + a, (c >> 1) & 1);
             tc_fence_after();
-            for (int kb = 0; kb < nk; ++kb) {
+            for (int kb = part; kb < nk; kb += N_DRAIN / 4) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + a * SCH + 32 * kb, v);
                 const int col0 = (4 * c + kb) * 32;
@@ -594,20 +597,23 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
             for (int j = n_pre; j < n_blk; ++j) v_load(j);
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = F16, both K-major, M = 64, N = 32; K = 16 per instruction = 32 bytes
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            // instruction descriptors: D = F32, A = B = F16, both K-major, M = 64; K = 16 per instruction = 32 bytes.  A V slot holds
+            // V_hi^T (32 rows of 128 B) and V_lo^T right behind it, i.e. ONE K-major operand of N = 64 rows: P_hi [V_hi | V_lo] is a
+            // single N = 64 MMA (the 44-cycle floor of a small MMA either way) into columns 0..63 of O, P_lo V_hi an N = 32 MMA into
+            // columns 0..31 -- two instructions per k-step instead of three; the epilogue adds the two column blocks.
+            constexpr uint32_t idesc32 = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            constexpr uint32_t idesc64 = (1u << 4) | ((uint32_t)(2 * D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
             for (int j = 0; j < n_blk; ++j) {
                 const int s = v_slot(j);
                 mbar_wait(vfull + s, v_use(j) & 1);
                 tc_fence_after();
                 uint8_t *st = stage + s * V_SLOT;
                 const uint64_t ph = umma_desc(sm + j * 16384), pl = umma_desc(sm + j * 16384 + 8192);
-                const uint64_t vh = umma_desc(st), vl = umma_desc(st + 4096);
+                const uint64_t vh = umma_desc(st);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    umma_f16(tmem_o, ph + 2 * k, vh + 2 * k, idesc, (j | k) != 0);
-                    umma_f16(tmem_o, ph + 2 * k, vl + 2 * k, idesc, 1);
-                    umma_f16(tmem_o, pl + 2 * k, vh + 2 * k, idesc, 1);
+                    umma_f16(tmem_o, ph + 2 * k, vh + 2 * k, idesc64, (j | k) != 0);
+                    umma_f16(tmem_o, pl + 2 * k, vh + 2 * k, idesc32, 1);
                 }
                 umma_commit(vempty + s);
             }
@@ -631,8 +637,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
         mbar_wait(pvdone, 0);
         tc_fence_after();
         if (warp == 4 && lane == 0 && p.dbg && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) p.dbg[3] = clock64();
-        float v[32];
-        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16), v);
+        float v[32], v2[32];
+        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16), v);             // P_hi V_hi + P_lo V_hi
+        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16) + D, v2);        // P_hi V_lo
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[i];
         if (lane < 16 && r < n_rows) {
             const float f = w0 / (rsum[r] * (P_SCALE * V_SCALE));
             float *dst = p.acc + ((size_t)b * p.Sq + row0 + r) * C + h * D;
