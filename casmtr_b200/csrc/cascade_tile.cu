@@ -246,6 +246,9 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 }
             }
             // ---- softmax over the 100 candidates per sibling
+            // (the weights stay un-normalised: the message is linear in them, 1 / sum scales the output at the end, and the row sums'
+            // shuffle chains travel under the A.V loop)
+            float inv_sum[4];
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
                 float mx = fmaxf(fmaxf(sc[0][f], sc[1][f]), fmaxf(sc[2][f], sc[3][f]));
@@ -253,10 +256,7 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 float sum = 0.f;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { sc[r][f] = exp_neg(sc[r][f] - mx); sum += sc[r][f]; }
-                sum = warp_sum(sum);
-                const float inv = 1.0f / sum;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) sc[r][f] *= inv;
+                inv_sum[f] = 1.0f / warp_sum(sum);
             }
             __syncwarp();
 #pragma unroll
@@ -303,7 +303,8 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 const float recv = __shfl_xor_sync(FULL_MASK, (g & 1) ? r2[0][c] : r2[1][c], 8);
                 m4[c] = ((g & 1) ? r2[1][c] : r2[0][c]) + recv;
             }
-            *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+            const float inv = g == 0 ? inv_sum[0] : g == 1 ? inv_sum[1] : g == 2 ? inv_sum[2] : inv_sum[3];      // the lane holds sibling g's output
+            *reinterpret_cast<float4 *>(p.out + ((size_t)b * L0 + QTOK(g)) * C + h * D + 4 * dq) = make_float4(m4[0] * inv, m4[1] * inv, m4[2] * inv, m4[3] * inv);
 
             // ---- upsampled_idx (:450): the window's key token indices, identical for the 4 siblings
             if (p.upsampled_idx != nullptr && h == 0) {

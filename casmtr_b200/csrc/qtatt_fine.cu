@@ -209,6 +209,8 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
 
     // ---- softmax -> a[r][f]; sc[r][f] becomes the selection score (>= 0, -1 = invalid)
     float a[R][4];
+    // (Deferring the 1 / sum scaling to the output, as cascade_tile.cu does, was measured here and lost: the compiler then hoists all
+    // streamed V loads above the soft-max, 72 -> 122 registers, last level 84 -> 85 us uncapped and 93 us capped with spills.)
     if (!TYPE_A) {      // over all candidates of sibling f
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
@@ -728,8 +730,9 @@ int launch_cta_t(const FineParams &p, cudaStream_t stream) {
 }
 
 // grid.x covers the (parent, head) items of one batch element, grid.y = batch
+// (QTAtt levels: at most 85 registers = the 24 warps per SM that the 8.5 KB slabs allow at kp = 16; 84.4 -> 83.4 us per launch)
 template <int KP, int R, bool CASCADE, bool TYPE_A, bool DO_TOPK, bool PE = false>
-__global__ void __launch_bounds__(256) quad_attention_kernel(FineParams p, int warps_per_cta) {
+__global__ void __launch_bounds__(256, (CASCADE || R > 2) ? 1 : 3) quad_attention_kernel(FineParams p, int warps_per_cta) {
     pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
