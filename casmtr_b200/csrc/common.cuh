@@ -117,5 +117,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Bitonic sort of one fp32 value per lane, descending (lane 0 ends with the largest): 15 shuffle + FMNMX steps (the compare
+// direction is a predicate of the lane index, which FMNMX takes as its min / max selector).
+__device__ __forceinline__ float warp_sort_desc(float v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const float o = __shfl_xor_sync(FULL_MASK, v, stride);
+            const bool up = (lane & size) != 0;                  // this block of `size` lanes sorts ascending
+            const bool lower = (lane & stride) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+
 // exp(x) for x <= 0 as used by every softmax here: one FMUL + EX2 (2 ulp).
 __device__ __forceinline__ float exp_neg(float x) { return exp2f(x * LOG2E_F); }

@@ -557,13 +557,13 @@ __global__ void __launch_bounds__(128, SV ? 9 : 1) quad_cta_kernel(FineParams p)
     // ---- top-k of sibling f for the next level
     if (DO_TOPK) {
         const int k = p.topk;
-        unsigned key[R], km = 0;
+        unsigned key[R];
+        float lmax = -1.f;
 #pragma unroll
-        for (int r = 0; r < R; ++r) { key[r] = okey(sel[r]); km = max(km, key[r]); }
-        int above = 0;
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) above += __shfl_sync(FULL_MASK, km, l) > km;
-        const unsigned T = __reduce_min_sync(FULL_MASK, (above < k && km > 0) ? km : 0xffffffffu);   // k-th largest lane maximum
+        for (int r = 0; r < R; ++r) { key[r] = okey(sel[r]); lmax = fmaxf(lmax, sel[r]); }
+        // T = k-th largest lane maximum (at least k candidates are >= T): a 15-step bitonic sort of the lane maxima instead of 32
+        // rounds of rank counting (16 % of this kernel's instructions, scripts/ncu_lines.py)
+        const unsigned T = okey(__shfl_sync(FULL_MASK, warp_sort_desc(lmax, lane), (k - 1) & 31));
         int n = 0;
         bool sv[R];
 #pragma unroll
