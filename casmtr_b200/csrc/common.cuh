@@ -79,6 +79,29 @@ int casmtr_sm_count();          // SM count of the current device (cached per de
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Division of a non-negative int32 by a launch-time constant as multiply-high + shift (the grid widths and head counts the
+// kernels divide by are runtime values, and an integer division is ~20 instructions on the SIMT cores).  Exact for 0 <= n < 2^31.
+struct FastDiv {
+    unsigned mul, shr;          // mul == 0: divisor 1
+    int d;
+#ifdef __CUDACC__
+    __device__ __forceinline__ int div(int n) const { return mul ? (int)(__umulhi((unsigned)n, mul) >> shr) : n; }
+    __device__ __forceinline__ void divmod(int n, int &q, int &r) const { q = div(n); r = n - q * d; }
+#endif
+};
+static inline FastDiv make_fastdiv(int div) {
+    FastDiv f;
+    f.mul = 0; f.shr = 0; f.d = div > 0 ? div : 1;
+    if (div > 1) {
+        int lg = 0;
+        while ((1ll << lg) < div) ++lg;                           // ceil(log2 d)
+        const unsigned long long p2 = 1ull << (31 + lg);
+        f.mul = (unsigned)((p2 + (unsigned)div - 1) / (unsigned)div);
+        f.shr = (unsigned)(lg - 1);
+    }
+    return f;
+}
+
 // Bump allocator over the caller's workspace.
 struct Workspace {
     char *base;

@@ -107,6 +107,8 @@ struct FineParams {
     int type_a, final_level;
     const int *item_list;       // NULL, or device list of cells (b * Np + parent) to process for every head (cascade fallback)
     const int *item_count;      // device int: length of item_list
+    // filled by launch_quad_attention: the divisors of the kernels' index arithmetic
+    FastDiv d_nh, d_wp, d_np, d_wprev, d_wv, d_win;     // nh, w0 / 2, (h0 / 2) (w0 / 2), w_prev, w1 / 2, win
 };
 int launch_quad_attention(const FineParams &p, cudaStream_t stream);
 

@@ -78,7 +78,7 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
     const int g = lane >> 3, dq = lane & 7;
     const int wp = p.w0 >> 1;
     const int Np = (p.h0 >> 1) * wp;
-    const int py = parent / wp, px = parent - py * wp;
+    const int py = p.d_wp.div(parent), px = parent - py * wp;
     const int C = p.nh * D, L0 = p.h0 * p.w0, L1 = p.h1 * p.w1;
     const int kp = KP ? KP : p.kp, KC = 4 * kp;
     const float scale = rsqrtf((float)D);
@@ -108,8 +108,11 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
             if (p.next_idx != nullptr) {             // window derived from the parent's match on the previous grid
                 const int hv = p.h1 >> 1, wv = p.w1 >> 1;
                 const int idx = (int)__ldg(p.next_idx + (size_t)b * Np + parent);
-                const int r0 = window_origin(idx / wv, p.win, hv), c0 = window_origin(idx % wv, p.win, wv);
-                base = 2 * (r0 + lane / p.win) * p.w1 + 2 * (c0 + lane % p.win);
+                int ir, ic, lr, lc;
+                p.d_wv.divmod(idx, ir, ic);
+                p.d_win.divmod(lane, lr, lc);
+                const int r0 = window_origin(ir, p.win, hv), c0 = window_origin(ic, p.win, wv);
+                base = 2 * (r0 + lr) * p.w1 + 2 * (c0 + lc);
             } else {
                 const int64_t *tp = p.topk_pos + (((size_t)b * Np + parent) * kp + lane) * 2;
                 base = (int)(2 * tp[0] * p.w1 + 2 * tp[1]);
@@ -117,7 +120,7 @@ __device__ __forceinline__ void quad_item(const FineParams &p, float *Ks, int b,
         } else {
             const size_t o = (((size_t)b * Np + parent) * p.nh + h) * kp + lane;
             const int idx = p.prev_idx[o];
-            const int r = idx / p.w_prev;
+            const int r = p.d_wprev.div(idx);
             base = 2 * r * p.w1 + 2 * (idx - r * p.w_prev);
             if (TYPE_A) pscore = p.prev_score[o];
         }
@@ -447,8 +450,8 @@ __global__ void __launch_bounds__(128, SV ? 9 : 1) quad_cta_kernel(FineParams p)
     const int wp = p.w0 >> 1;
     const int Np = (p.h0 >> 1) * wp;
     const int b = blockIdx.y;
-    const int parent = blockIdx.x / (unsigned)p.nh, h = blockIdx.x - parent * p.nh;
-    const int py = parent / wp, px = parent - py * wp;
+    const int parent = p.d_nh.div((int)blockIdx.x), h = blockIdx.x - parent * p.nh;
+    const int py = p.d_wp.div(parent), px = parent - py * wp;
     const int C = p.nh * D, L0 = p.h0 * p.w0, L1 = p.h1 * p.w1;
     const int kp = KP ? KP : p.kp, KC = 4 * kp;
     const float scale = rsqrtf((float)D);
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(128, SV ? 9 : 1) quad_cta_kernel(FineParams p)
     if (lane < kp) {
         const size_t o = (((size_t)b * Np + parent) * p.nh + h) * kp + lane;
         const int idx = p.prev_idx[o];
-        const int r = idx / p.w_prev;
+        const int r = p.d_wprev.div(idx);
         base = 2 * r * p.w1 + 2 * (idx - r * p.w_prev);
         if (TYPE_A) pscore = p.prev_score[o];
     }
@@ -739,13 +742,14 @@ __global__ void __launch_bounds__(256, (CASCADE || R > 2) ? 1 : 3) quad_attentio
     const int Np = (p.h0 >> 1) * (p.w0 >> 1);
     const unsigned item = blockIdx.x * (unsigned)warps_per_cta + warp;
     if (item >= (unsigned)(Np * p.nh)) return;
-    const int parent = item / (unsigned)p.nh, h = item - parent * p.nh;
+    const int parent = p.d_nh.div((int)item), h = item - parent * p.nh;
     quad_item<KP, R, CASCADE, TYPE_A, DO_TOPK, PE>(p, smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp), blockIdx.y, parent, h, lane);
 }
 
 // persistent variant over a device-side list of cells (b * Np + parent), all heads of each: the cascade fallback
+// (two 8-warp CTAs per SM: 128 registers; one more register halves the resident warps of this latency-bound kernel, 41 -> 49 us)
 template <int KP, int R, bool PE = false>
-__global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, int warps_per_cta) {
+__global__ void __launch_bounds__(256, 2) quad_attention_list_kernel(FineParams p, int warps_per_cta) {
     pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -753,8 +757,10 @@ __global__ void __launch_bounds__(256) quad_attention_list_kernel(FineParams p, 
     const int n = *p.item_count * p.nh;
     float *slab = smem + (size_t)warp * warp_slab_floats(KP ? KP : p.kp);
     for (int i = blockIdx.x * warps_per_cta + warp; i < n; i += gridDim.x * warps_per_cta) {
-        const int cell = p.item_list[i / p.nh], h = i % p.nh;
-        quad_item<KP, R, true, false, false, PE>(p, slab, cell / Np, cell % Np, h, lane);
+        int ci, h, cb, cp;
+        p.d_nh.divmod(i, ci, h);
+        p.d_np.divmod(p.item_list[ci], cb, cp);
+        quad_item<KP, R, true, false, false, PE>(p, slab, cb, cp, h, lane);
         __syncwarp();
     }
 }
@@ -826,9 +832,17 @@ int launch_by_flags(const FineParams &p, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_quad_attention(const FineParams &p, cudaStream_t stream) {
-    CASMTR_REQUIRE(p.kp >= 1 && p.kp <= 32, CASMTR_E_UNSUPPORTED, "parent candidate count %d must be in [1,32]", p.kp);
-    CASMTR_REQUIRE((p.h0 % 2) == 0 && (p.w0 % 2) == 0, CASMTR_E_INVALID, "query grid %dx%d must be even", p.h0, p.w0);
+int launch_quad_attention(const FineParams &p_in, cudaStream_t stream) {
+    CASMTR_REQUIRE(p_in.kp >= 1 && p_in.kp <= 32, CASMTR_E_UNSUPPORTED, "parent candidate count %d must be in [1,32]", p_in.kp);
+    CASMTR_REQUIRE((p_in.h0 % 2) == 0 && (p_in.w0 % 2) == 0, CASMTR_E_INVALID, "query grid %dx%d must be even", p_in.h0, p_in.w0);
+    CASMTR_REQUIRE(p_in.nh >= 1 && p_in.h0 >= 2 && p_in.w0 >= 2 && p_in.h1 >= 2 && p_in.w1 >= 2, CASMTR_E_INVALID, "quad attention: empty grid");
+    FineParams p = p_in;                             // + the multiply-shift forms of the divisors the kernels use
+    p.d_nh = make_fastdiv(p.nh);
+    p.d_wp = make_fastdiv(p.w0 / 2);
+    p.d_np = make_fastdiv((p.h0 / 2) * (p.w0 / 2));
+    p.d_wprev = make_fastdiv(p.w_prev > 0 ? p.w_prev : 1);
+    p.d_wv = make_fastdiv(p.w1 / 2);
+    p.d_win = make_fastdiv(p.win > 0 ? p.win : 1);
     if (p.item_list) {                               // cascade fallback cells of the tile kernel
         CASMTR_REQUIRE((p.topk_pos || p.next_idx) && p.kp == 25, CASMTR_E_INVALID, "item lists are a cascade (k = 25) feature");
         return p.pe.w_tab ? launch_list_t<25, 4, true>(p, stream) : launch_list_t<25, 4, false>(p, stream);
