@@ -185,8 +185,8 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             float sc[4][4];
             {
                 float2 acc[4][4];
-                unsigned krow[4];
-                int ksw[4];
+                unsigned kaddr[4];                      // shared address of the row's swizzled chunk 0: chunk j is at kaddr ^ (j << 4)
+                const unsigned kt = smem_u32(Kt);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -194,8 +194,7 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     const int c = min(32 * r + lane, KC - 1);
                     const int kk = c >> 2, f = c & 3;
                     const int trow = (2 * (wy0 + kk / 5) + (f >> 1)) * TW + 2 * (wx0 + kk % 5) + (f & 1);
-                    krow[r] = trow * D;
-                    ksw[r] = trow & 7;
+                    kaddr[r] = kt + (unsigned)trow * (D * 4) + ((unsigned)(trow & 7) << 4);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -204,7 +203,7 @@ cascade_att_tile_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + ((f >> 1) * 2 * TP + (f & 1)) * D + 4 * j);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const float4 kv = *reinterpret_cast<const float4 *>(Kt + krow[r] + 4 * (j ^ ksw[r]));
+                        const float4 kv = lds128(kaddr[r] ^ (unsigned)(j << 4));
 #pragma unroll
                         for (int f = 0; f < 4; ++f) acc[r][f] = dot4p(qv[f], kv, acc[r][f]);
                     }

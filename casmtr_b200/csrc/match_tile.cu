@@ -160,8 +160,7 @@ __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel
             for (int f = 0; f < 4; ++f) acc[r][f] = make_float2(0.f, 0.f);
         bool use = false;
         CellMeta m;
-        unsigned krow[4];
-        int ksw[4];
+        unsigned koff[4];                               // byte offset of the row's swizzled chunk 0 inside a key tile
         for (int sl = 0; sl < NS; ++sl, ++step) {
             const int s = step % NSTAGE;
             mbar_wait(full + s, (step / NSTAGE) & 1);
@@ -176,13 +175,15 @@ __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel
                         const int c = min(32 * r + lane, KC - 1);
                         const int kk = c >> 2, f = c & 3;
                         const int trow = (2 * (m.wy0 + kk / 5) + (f >> 1)) * TW + 2 * (m.wx0 + kk % 5) + (f & 1);
-                        krow[r] = trow * D;
-                        ksw[r] = trow & 7;
+                        koff[r] = (unsigned)trow * (D * 4) + ((unsigned)(trow & 7) << 4);
                     }
                 }
             }
             if (use) {
-                const float *Kt = (const float *)(sm + s * STAGE_BYTES);
+                const unsigned kt = smem_u32(sm + s * STAGE_BYTES);
+                unsigned kaddr[4];                      // chunk j of the row is at kaddr ^ (j << 4) (tma.cuh, lds128)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) kaddr[r] = kt + koff[r];
                 const float *Qs = (const float *)(sm + s * STAGE_BYTES + KEY_BYTES) + ((2 * ly) * (2 * TP) + 2 * lx) * D;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__((NCONS + 1) * 32, 1) cascade_match_tile_kernel
                     for (int f = 0; f < 4; ++f) qv[f] = *reinterpret_cast<const float4 *>(Qs + ((f >> 1) * 2 * TP + (f & 1)) * D + 4 * j);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const float4 kv = *reinterpret_cast<const float4 *>(Kt + krow[r] + 4 * (j ^ ksw[r]));
+                        const float4 kv = lds128(kaddr[r] ^ (unsigned)(j << 4));
 #pragma unroll
                         for (int f = 0; f < 4; ++f) acc[r][f] = dot4p(qv[f], kv, acc[r][f]);
                     }

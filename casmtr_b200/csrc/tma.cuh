@@ -13,6 +13,15 @@ __device__ __forceinline__ float2 dot4p(const float4 q, const float4 k, float2 a
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// 16-byte load at a 32-bit shared-memory address.  The tile kernels read 128-byte-swizzled rows: chunk j of row r lives at
+// chunk j ^ (r & 7), and with the row's 128-byte-aligned address pre-combined with (r & 7) << 4 the address of logical chunk j
+// is ONE xor with an immediate (the compiler's own form of the same expression is xor-or + add per load).
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
