@@ -15,6 +15,9 @@
 // of the token-major feature map, mostly served by L2 (the maps are 11-22 MB).  A warp first issues ALL
 // of its gathers as 16-byte cp.async (LDGSTS) straight into its private shared-memory slab -- 8 lanes
 // per row, 4 rows per instruction, no registers held -- and only then computes:
+//   (Measured alternative, round 2: one cp.async.bulk -- TMA without a tensor map -- per 128-byte row, completed on a per-warp
+//   mbarrier, rows unswizzled and read in a per-lane rotated chunk order.  It removes ~130 of the ~1100 instructions of a last-level
+//   item and is 30 % SLOWER, 81 -> 107 us per launch: the copy engine's per-request cost dominates at 128 bytes per request.)
 //   Q.K^T    lane = candidate (round r: candidate 32r + lane).  K rows are XOR-swizzled in 16-byte chunks
 //            so the per-lane row reads are bank-conflict free; the 4 sibling q rows are broadcast reads,
 //            loaded once per chunk and reused across the rounds.  FMAs are issued as packed FFMA2
