@@ -49,6 +49,8 @@ SIGNATURES = {
     'casmtr_profile_enable': (C.c_int, [C.c_int]),
     'casmtr_profile_collect': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     'casmtr_kernel_kind_name': (C.c_char_p, [C.c_int]),
+    'casmtr_plan_dense_tiles': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    'casmtr_fastdiv': (C.c_int, [C.c_int, C.POINTER(C.c_uint)]),
     'casmtr_score5d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_value_agg_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     'casmtr_score3d_fwd': (C.c_int, [c_float_p, c_float_p, c_i64_p, c_float_p] + [C.c_int] * 5 + [C.c_void_p]),

@@ -187,6 +187,19 @@ const char *casmtr_kernel_kind_name(int kind) { return kind >= 0 && kind < CASMT
 
 int casmtr_version(void) { return CASMTR_VERSION; }
 
+int casmtr_plan_dense_tiles(int rows, int bh, int n_sm, int out[3]) {
+    CASMTR_REQUIRE(out != nullptr && rows >= 1 && bh >= 1 && n_sm >= 1, CASMTR_E_INVALID, "plan_dense_tiles: rows=%d bh=%d n_sm=%d", rows, bh, n_sm);
+    coarse_tc_row_tiles(rows, bh, n_sm, out[0], out[1], out[2]);
+    return CASMTR_OK;
+}
+
+int casmtr_fastdiv(int d, unsigned out[2]) {
+    CASMTR_REQUIRE(out != nullptr && d >= 1, CASMTR_E_INVALID, "fastdiv: divisor %d", d);
+    const FastDiv f = make_fastdiv(d);
+    out[0] = f.mul; out[1] = f.shr;
+    return CASMTR_OK;
+}
+
 const char *casmtr_last_error_string(void) { return g_err; }
 
 int casmtr_device_info(int *sm_count, size_t *l2_bytes) {

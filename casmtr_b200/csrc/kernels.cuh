@@ -55,6 +55,7 @@ int launch_qtatt_coarse(const CoarseParams &p, cudaStream_t stream);
 bool coarse_tc_applicable(int Sq, int Sk, int topk);
 size_t coarse_tc_workspace_floats(int B, int Sq, int Sk, int C);
 int launch_qtatt_coarse_tc(const CoarseParams &p, float *ws, cudaStream_t stream);
+void coarse_tc_row_tiles(int Sq, int bh, int n_sm, int &n_big, int &n_small, int &rows_small);   // the kernel's row tiling (host logic)
 struct CoarseTcOperands { float *q_lo, *k_lo; unsigned short *vt_hi, *vt_lo; int Sp; };
 CoarseTcOperands coarse_tc_operands(float *ws, int B, int Sq, int Sk, int C);      // where those operands live inside tc_ws
 

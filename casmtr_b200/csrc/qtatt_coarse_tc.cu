@@ -771,6 +771,8 @@ int launch_variant(const CoarseTcMaps &maps, const TcParams &tp, bool type_a, in
 
 }  // namespace
 
+void coarse_tc_row_tiles(int Sq, int bh, int n_sm, int &n_big, int &n_small, int &rows_small) { tc_row_tiles(Sq, bh, n_sm, n_big, n_small, rows_small); }
+
 bool coarse_tc_applicable(int Sq, int Sk, int topk) {
     static const bool env_on = [] { const char *e = getenv("CASMTR_COARSE_TC"); return !(e && e[0] == '0'); }();
     int nv, n_kb;

@@ -88,6 +88,13 @@ CASMTR_API int casmtr_profile_enable(int on);
  * HOST arrays (CASMTR_K_COUNT entries each; either may be NULL) and clears the record list. */
 CASMTR_API int casmtr_profile_collect(double *ms_by_kind, uint64_t *launches_by_kind);
 CASMTR_API const char *casmtr_kernel_kind_name(int kind);
+/* Host-only introspection of two launch-time computations (no device needed; used by the CPU tests):
+ *  casmtr_plan_dense_tiles: the row tiling the tensor-core coarsest level uses for `rows` query rows per (batch, head), `bh` of them, on
+ *    `n_sm` SMs: out[0] tiles of 64 rows, then out[1] tiles of out[2] rows each (every row is covered exactly once, in order).
+ *  casmtr_fastdiv: the multiply-high / shift pair the kernels divide by `d` with: n / d == umulhi(n, out[0]) >> out[1] for 0 <= n < 2^31
+ *    (out[0] == 0: d == 1). */
+CASMTR_API int casmtr_plan_dense_tiles(int rows, int bh, int n_sm, int out[3]);
+CASMTR_API int casmtr_fastdiv(int d, unsigned out[2]);
 
 /* ---------------------------------------------------------------- op-level drop-ins (R1-R3) */
 
