@@ -318,6 +318,33 @@ def qtatt_call_stats(prof, wl, steps, peak, simt_peak):
                             {'layout_pool': round(1e3 * lay_ms / calls, 2)}}
 
 
+def qtatt_graph_stats(hp, dev_in, wl, timed, steps, peak, simt_peak):
+    """All QTAttB calls of a step (no cascade, no matching) captured as one CUDA graph and replayed: device time per call-equivalent."""
+    import torch
+
+    def calls():
+        for i, call in enumerate(dev_in['qt']):
+            hp.run_qt(i, call)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(3):
+            calls()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g), torch.no_grad():
+        calls()
+    for _ in range(3):
+        g.replay()
+    ms = timed(g.replay, steps)
+    n = wl.qt_layers * wl.B
+    call_ms = ms / n
+    by, fl = wl.bytes_qtatt_call(), wl.flops_qtatt_call()
+    return {'us_per_call_equivalent': round(1e3 * call_ms, 2), 'ms_all_calls': round(ms, 4), 'calls': n,
+            'frac_of_hbm_peak': round(by / call_ms / 1e6 / peak, 4), 'frac_of_fp32_simt_peak': round(fl / call_ms / 1e9 / simt_peak, 4)}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from casmtr_b200 import _lib
@@ -474,6 +501,12 @@ def run_ours(args):
     props = torch.cuda.get_device_properties(dev)
     simt_peak = props.multi_processor_count * 128 * 2 * ((clocks or {}).get('sm_mhz') or 1965.0) * 1e6 / 1e12      # TFLOP/s at the clock under load
     qtatt_call = qtatt_call_stats(prof, wl, args.steps, peak, simt_peak)
+    # the same calls alone as ONE CUDA graph (no per-kernel event pairs, launch chaining on): the call-equivalent a step really pays
+    if not args.no_graph and n_gpus == 1 and rank == 0:
+        try:
+            qtatt_call['graph_replay'] = qtatt_graph_stats(hp, dev_in, wl, timed, args.steps, peak, simt_peak)
+        except Exception as e:      # noqa: BLE001
+            qtatt_call['graph_replay'] = {'error': str(e)[:200]}
 
     # ---- batch sweep: the same step at 2 / 4 / 8 pairs per launch set
     batch_sweep = None

@@ -22,6 +22,8 @@ def main(path):
     q = d.get('qtatt_call_roofline')
     if q:
         print(f"   QTAttB call-equivalent {q['us_per_call_equivalent']} us  hbm {q['frac_of_hbm_peak']}  simt {q['frac_of_fp32_simt_peak']}  {q['us_by_kernel']}")
+        if q.get('graph_replay'):
+            print(f"   QTAttB calls alone as one graph: {q['graph_replay']}")
     r = d.get('roofline')
     if r:
         print(f"   roofline {r['kernel']}: {r['achieved']} GB/s frac {r['frac']}  {r['ms_per_launch']} ms/launch")
