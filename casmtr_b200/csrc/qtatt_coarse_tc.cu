@@ -597,24 +597,21 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
             for (int j = n_pre; j < n_blk; ++j) v_load(j);
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptors: D = F32, A = B = F16, both K-major, M = 64; K = 16 per instruction = 32 bytes.  A V slot holds
-            // V_hi^T (32 rows of 128 B) and V_lo^T right behind it, i.e. ONE K-major operand of N = 64 rows: P_hi [V_hi | V_lo] is a
-            // single N = 64 MMA (the 44-cycle floor of a small MMA either way) into columns 0..63 of O, P_lo V_hi an N = 32 MMA into
-            // columns 0..31 -- two instructions per k-step instead of three; the epilogue adds the two column blocks.
-            constexpr uint32_t idesc32 = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-            constexpr uint32_t idesc64 = (1u << 4) | ((uint32_t)(2 * D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            // instruction descriptor: D = F32, A = B = F16, both K-major, K = 16 per instruction = 32 bytes.  Both operands are stacked: a V
+            // slot holds V_hi^T (32 rows of 128 B) with V_lo^T right behind it = ONE K-major B operand of N = 64 rows, and the P_hi tile of
+            // a 64-key block (64 rows of 128 B) has its P_lo tile right behind it = ONE A operand of M = 128 rows.  A single 128 x 64 x 16
+            // MMA per k-step therefore yields P_hi V_hi | P_hi V_lo in accumulator rows 0..63 and P_lo V_hi | P_lo V_lo in rows 64..127
+            // (48 cycles against 3 x 44 for three 64 x 32 MMAs: small MMAs cost their issue floor); the epilogue adds the four blocks.
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(2 * D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int j = 0; j < n_blk; ++j) {
                 const int s = v_slot(j);
                 mbar_wait(vfull + s, v_use(j) & 1);
                 tc_fence_after();
                 uint8_t *st = stage + s * V_SLOT;
-                const uint64_t ph = umma_desc(sm + j * 16384), pl = umma_desc(sm + j * 16384 + 8192);
+                const uint64_t ph = umma_desc(sm + j * 16384);
                 const uint64_t vh = umma_desc(st);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    umma_f16(tmem_o, ph + 2 * k, vh + 2 * k, idesc64, (j | k) != 0);
-                    umma_f16(tmem_o, pl + 2 * k, vh + 2 * k, idesc32, 1);
-                }
+                for (int k = 0; k < 4; ++k) umma_f16(tmem_o, ph + 2 * k, vh + 2 * k, idesc, (j | k) != 0);
                 umma_commit(vempty + s);
             }
             umma_commit(pvdone);
@@ -623,8 +620,9 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
 
     // ================================================================ epilogue: O / (scales * row sum) * level weight -> acc
     if (warp >= 4 && warp < 8) {
+        // M = 128 accumulator: row i in TMEM lane i.  Lane quarters 0, 1 (warps 4, 5) hold the P_hi rows 0..63, quarters 2, 3 (warps 6, 7)
+        // the P_lo rows of the same queries: those go through 8 KB of the (now idle) staging area to the warps that own the rows.
         const int q = warp & 3;
-        const int r = 16 * q + lane;
         float w0 = 1.f;
         if (p.level_weight) {                           // softmax over the level weights (:264)
             float mx = -INFINITY, den = 0.f;
@@ -638,16 +636,26 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
         tc_fence_after();
         if (warp == 4 && lane == 0 && p.dbg && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) p.dbg[3] = clock64();
         float v[32], v2[32];
-        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16), v);             // P_hi V_hi + P_lo V_hi
-        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16) + D, v2);        // P_hi V_lo
+        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16), v);             // x V_hi
+        tmem_ld32(tmem_o + ((uint32_t)(32 * q) << 16) + D, v2);        // x V_lo
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += v2[i];
-        if (lane < 16 && r < n_rows) {
+        const int r = 32 * (q & 1) + lane;                             // query row of this lane (both halves)
+        float *xch = reinterpret_cast<float *>(stage) + r * 32;        // [64 rows][32], 16-byte chunks swizzled by the row
+        if (q >= 2) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<float4 *>(xch + ((ch ^ (r & 7)) << 2)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");              // warps 4..7 only
+        if (q < 2 && r < n_rows) {
             const float f = w0 / (rsum[r] * (P_SCALE * V_SCALE));
             float *dst = p.acc + ((size_t)b * p.Sq + row0 + r) * C + h * D;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-                *reinterpret_cast<float4 *>(dst + 4 * ch) = make_float4(v[4 * ch] * f, v[4 * ch + 1] * f, v[4 * ch + 2] * f, v[4 * ch + 3] * f);
+            for (int ch = 0; ch < 8; ++ch) {
+                const float4 t = *reinterpret_cast<const float4 *>(xch + ((ch ^ (r & 7)) << 2));
+                *reinterpret_cast<float4 *>(dst + 4 * ch) = make_float4((v[4 * ch] + t.x) * f, (v[4 * ch + 1] + t.y) * f, (v[4 * ch + 2] + t.z) * f, (v[4 * ch + 3] + t.w) * f);
+            }
         }
     }
     tc_fence_before();
