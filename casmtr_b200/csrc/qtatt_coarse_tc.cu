@@ -5,27 +5,32 @@
 // The SIMT kernel of qtatt_coarse.cu spends 1.2 K of its 5.1 K warp-instructions per query row on the two contractions (FFMA2
 // out of shared memory) and their tile traffic; here they cost the SM nothing but one elected thread issuing MMAs:
 //
-//   CTA = ROWS (64 or 32) query rows of one (batch, head), 512 threads, one CTA per SM (the score slab fills shared memory).
+//   CTA = up to 64 query rows of one (batch, head), 512 threads, one CTA per SM (the score slab fills shared memory).  Row tiles: 64-row
+//             tiles cut back to whole waves of SMs, the rows left over in every (batch, head) split evenly over one more wave of short
+//             tiles (tc_row_tiles) -- one image pair is 9 x 64 + 9 x 12 rows per head instead of 176 CTAs on 148 SMs.
 //   phase S   warp 0 = TMA producer: Q_hi / Q_lo and EVERY K_hi / K_lo tile at once -- the K operand of a 128-key chunk is loaded
 //             into the very slab bytes that chunk's scores will occupy (32 KB either way), so nothing waits for a ring slot.
-//             warp 1 = MMA issuer: per chunk 4 k-steps x 3 terms (hi*hi + hi*lo + lo*hi; x_lo = x - trunc_tf32(x) is precomputed
-//             by coarse_prep_kernel) of UMMA 64x128x8 (kind::tf32) into one of two TMEM accumulators.  warps 4-7 = drain:
-//             tcgen05.ld (one accumulator row per thread), * D^-1/2 log2(e), 16-byte stores into the SLAB over the K tiles the
-//             finished MMAs no longer need: k-blocks of 32 keys, each a [64 rows x 128 B] tile with the 128-byte swizzle.
-//   phase T   all 16 warps, one warp per row, two rows at a time, the row in registers (lane l holds keys 2l, 2l + 1 of every
-//             64-key block): max, P = 2^(s - max), sum; exact top-k without a sort of the row: the k-th largest of the 64
+//             warp 1 = MMA issuer: per chunk 4 k-steps x 3 terms (hi*hi + hi*lo + lo*hi; x_lo = x - trunc_tf32(x) comes from the pooling
+//             pass, layout.cu, or coarse_prep_kernel) of UMMA 64x128x8 (kind::tf32) into one of two TMEM accumulators.  warps 4-11 =
+//             drain, two warps per TMEM lane quarter taking alternate k-blocks: tcgen05.ld (one accumulator row per thread), * D^-1/2
+//             log2(e), 16-byte stores into the SLAB over the K tiles the finished MMAs no longer need: k-blocks of 32 keys, each a
+//             [64 rows x 128 B] tile with the 128-byte swizzle.
+//   phase T   all 16 warps, one warp per row, two rows at a time interleaved by hand, the row in registers (lane l holds keys 2l, 2l + 1
+//             of every 64-key block): max, P = 2^(s - max), sum; exact top-k without a sort of the row: the k-th largest of the 64
 //             lane-local top-2 values (two 32-lane bitonic sorts + one max = the upper half of their union) is a threshold T
 //             below the row's k-th largest value, the survivors {P >= T} (k <= n, typically n ~ 40) are compacted through a
-//             warp prefix sum and trimmed to exactly k by removing the minimum n - k times.  The k selected keys are emitted in
-//             list order; the order torch.topk would give them is restored only where the lists leave the library
-//             (topk_to_api_kernel).  P goes back into the row's own slab bytes as an fp16 PAIR: P * 2^14 = hi + lo, the two
-//             k-blocks (2 x 8 KB) that held the fp32 scores of 64 keys now hold a [64 rows x 64 keys] fp16 tile of hi and one of lo.
-//   phase PV  O[64 x 32] = P V over all keys as kind::f16 MMAs (K = 16 per instruction): V^T * 2^8 = hi + lo in fp16 likewise
-//             (coarse_prep_kernel), [32 dims x 64 keys] tiles through a 6-slot TMA ring whose first 4 slots are filled while
-//             phases S and T run; per 64-key block 4 k-steps x (P_hi V_hi + P_hi V_lo + P_lo V_hi), fp32 accumulation in TMEM.
-//             (A first version kept P in fp32 and ran TF32 MMAs in two passes over V with an in-place P -> P_lo rewrite in
-//             between: 3 x the V traffic through the ring and 2 x the MMAs; measured 35 K cycles per CTA against ~10 K.)
-//   epilogue  warps 4-7: O from TMEM, / (2^22 * row sum), * level weight, 128-byte row stores.
+//             warp prefix sum with straight-line predicated stores and trimmed to exactly k by removing the minimum (an integer
+//             REDUX: P >= 0) n - k times.  The k selected keys are emitted in list order; the order torch.topk would give them is
+//             restored only where the lists leave the library (topk_to_api_kernel).  P goes back into the row's own slab bytes as an
+//             fp16 PAIR: P * 2^14 = hi + lo, the two k-blocks (2 x 8 KB) that held the fp32 scores of 64 keys now hold a
+//             [64 rows x 64 keys] fp16 tile of hi and, right behind it, one of lo.
+//   phase PV  O = P V over all keys as kind::f16 MMAs (K = 16 per instruction) with BOTH operands stacked: [P_hi; P_lo] is one
+//             M = 128 A operand, V^T * 2^8 = hi + lo (fp16, [32 dims x 64 keys] tiles, hi then lo, through a 6-slot TMA ring whose
+//             first 4 slots are filled while phases S and T run) one N = 64 B operand: ONE 128x64x16 MMA per k-step yields all four
+//             partial products, fp32 accumulation in TMEM.  (First version: P in fp32, TF32 MMAs in two passes over V: 35 K cycles per
+//             CTA; three 64x32x16 MMAs per k-step: ~10 K; stacked: ~3 K.)
+//   epilogue  warps 4-7: the four blocks of O from TMEM (the P_lo rows cross lane quarters through 8 KB of the idle staging area),
+//             / (2^22 * row sum), * level weight, 128-byte row stores.
 // Accuracy: every product carries ~2^-21 relative error (error-compensated splits, fp32 accumulation in TMEM), like
 // coarse_match.cu; the top-k sets are those of the fp32 reference except at fp32 near-ties (tests/: sets + the tie rule).
 #include <cuda_fp16.h>
