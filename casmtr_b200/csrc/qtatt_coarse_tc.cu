@@ -182,7 +182,9 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
 // 32 keys (-inf in the padding columns).  Out: the same bytes hold P * 2^14 as fp16 hi / lo tiles of 64 keys (0 in the padding
 // columns), sum[] the row sums of P; the k selected entries of row rr: lanes with keep_a / keep_b set own list entries `lane` /
 // `lane + 32` (P value va / vb, key pa / pb), in no particular order.
-template <int NV, int RP>
+// TIGHT: the key count fills all NV / 2 blocks of 64 (n_blk == NV / 2, e.g. 676 keys with NV = 22): only the last block can hold
+// padding columns, so the per-block "is it there / is it full" tests of the unrolled loops fold away at compile time.
+template <int NV, int RP, bool TIGHT>
 __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row)[RP], const bool (&live)[RP], int Sk, int n_blk, int k, int lane,
                                                    float *const (&lv)[RP], int *const (&lp)[RP], float (&sum)[RP],
                                                    float (&va)[RP], float (&vb)[RP], int (&pa)[RP], int (&pb)[RP], bool (&keep_a)[RP], bool (&keep_b)[RP],
@@ -203,7 +205,7 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             float2 v = make_float2(-INFINITY, -INFINITY);
-            if (jb < n_blk) v = *reinterpret_cast<const float2 *>(sbase + jb * (2 * 64 * 32));
+            if (TIGHT || jb < n_blk) v = *reinterpret_cast<const float2 *>(sbase + jb * (2 * 64 * 32));
             e[rr][2 * jb] = v.x; e[rr][2 * jb + 1] = v.y;
             m[rr] = fmaxf(m[rr], fmaxf(v.x, v.y));
         }
@@ -221,14 +223,14 @@ __device__ __forceinline__ void rows_softmax_topk(uint8_t *slab, const int (&row
         for (int jb = 0; jb < NB; ++jb) {
             float e0 = ex2_approx(e[rr][2 * jb] - m[rr]), e1 = ex2_approx(e[rr][2 * jb + 1] - m[rr]);
             sum[rr] += e0 + e1;
-            if (jb < n_blk) {                                     // P * 2^14 = hi + lo (fp16 each), packed pairs
+            if (TIGHT || jb < n_blk) {                            // P * 2^14 = hi + lo (fp16 each), packed pairs
                 const uint32_t hi = pack_f16x2_rn(e0 * P_SCALE, e1 * P_SCALE);
                 const float2 hf = unpack_f16x2(hi);
                 const uint32_t lo = pack_f16x2_rn(fmaf(e0, P_SCALE, -hf.x), fmaf(e1, P_SCALE, -hf.y));
                 *reinterpret_cast<uint32_t *>(pbase[rr] + jb * 16384) = hi;
                 *reinterpret_cast<uint32_t *>(pbase[rr] + jb * 16384 + 8192) = lo;
             }
-            if (jb >= full_blk) {                                 // padding never takes part in the selection
+            if (TIGHT ? (jb == NB - 1 && full_blk < NB) : (jb >= full_blk)) {      // padding never takes part in the selection
                 if (64 * jb + t >= Sk) e0 = -1.f;
                 if (64 * jb + t + 1 >= Sk) e1 = -1.f;
             }
@@ -398,7 +400,7 @@ constexpr int N_VSLOT = STAGE_AREA / V_SLOT;    // 6
 constexpr int N_DRAIN = 8;                      // warps 4 .. 11 drain the S accumulators (phase S)
 constexpr int V_LEAD = 2;                       // block j lives in slot (j + V_LEAD) % N_VSLOT: slots 0, 1 hold the selection lists during phase T
 
-template <int NV, bool TYPE_A>
+template <int NV, bool TYPE_A, bool TIGHT>
 __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __grid_constant__ CoarseTcMaps maps, TcParams p) {
     pdl_sync();
     extern __shared__ uint8_t smem_raw[];
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) qtatt_coarse_tc_kernel(const __
                 lpp[rr] = lpos + rr * LIST_CAP;
             }
             long long *tdbg = (p.dbg && warp == 0 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == p.dbg_tile) ? p.dbg : nullptr;
-            rows_softmax_topk<NV, RP>(sm, row, live, p.Sk, p.n_kb / 2, p.topk, lane, lvp, lpp, sum, va, vb, pa, pb, keep_a, keep_b, tdbg);
+            rows_softmax_topk<NV, RP, TIGHT>(sm, row, live, p.Sk, p.n_kb / 2, p.topk, lane, lvp, lpp, sum, va, vb, pa, pb, keep_a, keep_b, tdbg);
 #pragma unroll
             for (int rr = 0; rr < RP; ++rr) {
                 if (!live[rr]) continue;                     // warp-uniform
@@ -770,14 +772,18 @@ int launch_variant(const CoarseTcMaps &maps, const TcParams &tp, bool type_a, in
     static PerDeviceOnce once;
     const int dev = PerDeviceOnce::device();
     if (!once.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(qtatt_coarse_tc_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qtatt_coarse_tc_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaSuccess;
+        for (auto kern : {qtatt_coarse_tc_kernel<NV, false, false>, qtatt_coarse_tc_kernel<NV, true, false>, qtatt_coarse_tc_kernel<NV, false, true>,
+                          qtatt_coarse_tc_kernel<NV, true, true>})
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { casmtr_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CASMTR_E_CUDA; }
         once.mark(dev);
     }
     LaunchScope ls(CASMTR_K_QT_COARSE, stream);
-    if (type_a) launch_k(qtatt_coarse_tc_kernel<NV, true>, dim3(grid_x, grid_y), NWARP * 32, smem, stream, maps, tp);
-    else launch_k(qtatt_coarse_tc_kernel<NV, false>, dim3(grid_x, grid_y), NWARP * 32, smem, stream, maps, tp);
+    const bool tight = tp.n_kb == NV;
+    auto kern = type_a ? (tight ? qtatt_coarse_tc_kernel<NV, true, true> : qtatt_coarse_tc_kernel<NV, true, false>)
+                       : (tight ? qtatt_coarse_tc_kernel<NV, false, true> : qtatt_coarse_tc_kernel<NV, false, false>);
+    launch_k(kern, dim3(grid_x, grid_y), NWARP * 32, smem, stream, maps, tp);
     CASMTR_CHECK_LAUNCH("qtatt_coarse_tc_kernel");
     return CASMTR_OK;
 }
