@@ -146,6 +146,11 @@ class Workload:
             return B * sum(self.bytes_cascade_att_call(s) * s['cross'] for s in self.stages) // sum(s['cross'] for s in self.stages)
         if kind == 'cascade_match':
             return self.P * sum(self.bytes_cascade_match_call(s) for s in self.stages) // len(self.stages)
+        if kind == 'layout' and self.entry == 'tokens':
+            # pooling pass of a QTAttB launch set: q, k, v read at L0; levels 1 and 2 written; plus the tensor-core level's operands
+            # (Q_lo, K_lo fp32 at L2, V^T as an fp16 pair padded to 8 keys)
+            Sp = (L2 + 7) // 8 * 8
+            return B * C * 4 * (3 * L0 + 3 * L1 + 3 * L2 + 2 * L2 + Sp)
         del s0
         return None
 
